@@ -1,0 +1,471 @@
+"""Atom model for the hot path: energies, radial matrix elements, Zeeman shifts.
+
+Host-side mirror of the parts of the reference's `AlkaliAtom`
+(arc/alkali_atom_functions.py) and `DivalentAtom` (arc/divalent_atom_functions.py)
+that the hot path calls, with the same method names, argument meaning and return
+units.  Element INPUT DATA (model-potential parameters, quantum defects, NIST
+levels, literature dipole elements) is read from data/atoms.json, exported from
+the reference's element classes by tools/export_atom_data.py.
+
+Radial matrix elements are computed on the GPU (radial.RadialBatch): a single
+`getRadialMatrixElement` call is a batch of one; `precompute_radial` evaluates a
+whole table in two kernel launches and fills the in-memory memo that stands in for
+the reference's per-element sqlite memo (alkali_atom_functions.py:1057-1065).
+"""
+import json
+import os
+from math import floor, sqrt
+
+import numpy as np
+from scipy.constants import physical_constants, m_e as C_m_e, h as C_h, e as C_e
+
+from .wigner import CG
+from . import radial as _radial
+
+_DATA = None
+_HARTREE_EV = 27.211_386_245_981      # alkali_atom_functions.py:1072
+
+
+def _data():
+    global _DATA
+    if _DATA is None:
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "atoms.json")
+        with open(p) as f:
+            _DATA = json.load(f)
+    return _DATA
+
+
+def printStateLetter(l):
+    return "SPDFGHIKLMNOQRTUVWXYZ"[l] if l < 21 else " l=%d" % l
+
+
+class AlkaliAtom:
+    """Data-backed atom.  `AlkaliAtom("Rubidium85")` or the named constructors below."""
+
+    divalent = False
+
+    def __init__(self, className, preferQuantumDefects=True, cpp_numerov=True, device=None):
+        d = _data()
+        className = d["aliases"].get(className, className)
+        if className not in d["atoms"]:
+            raise ValueError("unknown element class %r" % className)
+        a = d["atoms"][className]
+        self.className = className
+        self.elementName = a["elementName"]
+        self.Z, self.I, self.mass = a["Z"], a["I"], a["mass"]
+        self.alpha, self.alphaC = a["alpha"], a["alphaC"]
+        self.alpha_d_eff, self.alpha_q_eff = a["alpha_d_eff"], a["alpha_q_eff"]
+        self.a1, self.a2, self.a3, self.a4, self.rc = a["a1"], a["a2"], a["a3"], a["a4"], a["rc"]
+        self.gS, self.gL = a["gS"], a["gL"]
+        self.groundStateN = a["groundStateN"]
+        self.extraLevels = [tuple(x) for x in a["extraLevels"]]
+        self.minQuantumDefectN = a["minQuantumDefectN"]
+        self.NISTdataLevels = a["NISTdataLevels"]
+        self.scaledRydbergConstant = a["scaledRydbergConstant"]
+        self.ionisationEnergy = a["ionisationEnergy"]
+        self.quantumDefect = a["quantumDefect"]
+        self.preferQuantumDefects = preferQuantumDefects
+        self.cpp_numerov = cpp_numerov
+        self.device = device
+        self._raw = a
+        if not self.divalent:
+            self._saved = {(r[0], r[1]): r[2] for r in a.get("sEnergy", [])}
+            self._lit = {}
+            for r in a.get("literatureDME", []):
+                key = tuple(r[:6])
+                if key not in self._lit or r[7] < self._lit[key][1]:
+                    self._lit[key] = (r[6], r[7])
+        self._dipole = {}       # memo: (n1,l1,2j1,n2,l2,2j2[,s]) -> value, lower-energy state first
+        self._quadrupole = {}
+        self._energy = {}
+        self.gpu_kernel_launches = 0
+
+    # pickling support (saveCalculation, alkali_atom_functions.py:4136-4278): plain data only
+    def __getstate__(self):
+        return self.__dict__.copy()
+
+    # ------------------------------------------------------------------ energies
+    def _getSavedEnergy(self, n, l, j, s=0.5):
+        """alkali_atom_functions.py:880-892."""
+        if abs(j - (l - 0.5)) < 0.001:
+            return self._saved.get((n, l), 0.0)
+        elif abs(j - (l + 0.5)) < 0.001:
+            return self._saved.get((l, n), 0.0)
+        raise ValueError("j (=%.1f) is not equal to l+1/2 nor l-1/2 (l=%d)" % (j, l))
+
+    def getQuantumDefect(self, n, l, j, s=0.5):
+        """alkali_atom_functions.py:894-976."""
+        defect = 0.0
+        if l < 5:
+            c = self.quantumDefect[round(floor(s) + s + j - l)][l]
+            if l < 3 and abs(c[0]) < 1e-9 and self.Z != 1:
+                raise ValueError("Quantum defects for requested state "
+                                 "(n = %d, l = %d, j = %.1f, s=%.1f) are uknown. "
+                                 "Aborting calculation." % (n, l, j, s))
+            defect = (c[0] + c[1] / ((n - c[0]) ** 2) + c[2] / ((n - c[0]) ** 4)
+                      + c[3] / ((n - c[0]) ** 6) + c[4] / ((n - c[0]) ** 8)
+                      + c[5] / ((n - c[0]) ** 10))
+        else:
+            n = int(n)
+            l = int(l)
+            top_r4 = 3 * pow(n, 2) - (l * (l + 1))
+            bottom_r4 = 2 * pow(n, 5) * (l + 1.5) * (l + 1) * (l + 0.5) * l * (l - 0.5)
+            r4 = top_r4 / bottom_r4
+            top_r6 = (35 * pow(n, 4) - 5 * pow(n, 2) * (6 * l * (l + 1) - 5)
+                      + 3 * (l + 2) * (l + 1) * l * (l - 1))
+            bottom_r6 = (8 * pow(n, 7) * (l + 2.5) * (l + 2) * (l + 1.5) * (l + 1)
+                         * (l + 0.5) * l * (l - 0.5) * (l - 1) * (l - 1.5))
+            r6 = top_r6 / bottom_r6
+            defect = 0.5 * (self.alpha_d_eff * r4 + self.alpha_q_eff * r6) * pow(n, 3)
+        return defect
+
+    def _getHydrogenicCorrection(self, n, l, j, s=0.5):
+        """alkali_atom_functions.py:848-878."""
+        C_alpha = physical_constants["fine-structure constant"][0]
+        spinOrbit = (-self.scaledRydbergConstant * pow(C_alpha, 2)
+                     * (j * (j + 1) - l * (l + 1) - s * (s + 1))
+                     / (2 * l * (l + 0.5) * (l + 1) * pow(n, 3)))
+        relCorr = (self.scaledRydbergConstant / pow(n, 2)
+                   * (pow(C_alpha / n, 2) * ((n / (l + 0.5)) - 0.75)))
+        return spinOrbit + relCorr
+
+    def getEnergy(self, n, l, j, s=0.5):
+        """Level energy relative to the ionisation limit in eV
+        (alkali_atom_functions.py:794-846)."""
+        key = (n, l, j, s)
+        if key in self._energy:
+            return self._energy[key]
+        if l >= n:
+            raise ValueError("Requested energy for state l=%d >= n=%d !" % (l, n))
+        if ((not self.preferQuantumDefects or n < self.minQuantumDefectN)
+                and (n <= self.NISTdataLevels)
+                and (abs(self._getSavedEnergy(n, l, j, s=s)) > 1e-8)):
+            e = self._getSavedEnergy(n, l, j, s=s)
+        else:
+            defect = self.getQuantumDefect(n, l, j, s=s)
+            if l <= 4:
+                e = -self.scaledRydbergConstant / ((n - defect) ** 2)
+            else:
+                e = (-self.scaledRydbergConstant / ((n - defect) ** 2)
+                     - self._getHydrogenicCorrection(n, l, j, s=s))
+        self._energy[key] = e
+        return e
+
+    def getZeemanEnergyShift(self, l, j, mj, magneticFieldBz, s=0.5):
+        """Linear Zeeman shift in J (alkali_atom_functions.py:2647-2681)."""
+        prefactor = physical_constants["Bohr magneton"][0] * magneticFieldBz
+        gs = -physical_constants["electron g factor"][0]
+        sumOverMl = 0
+        for ml in np.linspace(mj - s, mj + s, round(2 * s + 1)):
+            if abs(ml) <= l + 0.1:
+                ms = mj - ml
+                sumOverMl += (ml + gs * ms) * abs(CG(l, ml, s, ms, j, mj)) ** 2
+        return prefactor * sumOverMl
+
+    # --------------------------------------------------------- radial wavefunctions
+    def _state_record(self, n, l, j, step=0.001):
+        """arcb200_state_t with the call-site arguments of
+        alkali_atom_functions.py:1068-1085 and 555-601 (s = 0.5 as there)."""
+        inner = max(4.0 * step, self.alphaC ** (1 / 3.0))
+        outer = 2.0 * n * (n + 15.0)
+        E = self.getEnergy(n, l, j) / _HARTREE_EV
+        mu = (self.mass - C_m_e) / self.mass
+        if l < 4:
+            p = (self.a1[l], self.a2[l], self.a3[l], self.a4[l], self.rc[l])
+        else:
+            p = (0.0, 0.0, 0.0, 0.0, 0.0)
+        return _radial.make_state(inner, outer, step, 0.01, 0.01, l, 0.5, j, E,
+                                  self.alphaC, self.alpha, self.Z, p[0], p[1], p[2],
+                                  p[3], p[4], mu)
+
+    def radialWavefunction(self, l, s, j, stateEnergy, innerLimit, outerLimit, step):
+        """(r, R(r)*r normalised) -- alkali_atom_functions.py:503-625, computed by the
+        batched CUDA Numerov kernel (batch of one)."""
+        innerLimit = max(4.0 * step, innerLimit)
+        mu = (self.mass - C_m_e) / self.mass
+        if l < 4:
+            p = (self.a1[l], self.a2[l], self.a3[l], self.a4[l], self.rc[l])
+        else:
+            p = (0.0, 0.0, 0.0, 0.0, 0.0)
+        rec = _radial.make_state(innerLimit, outerLimit, step, 0.01, 0.01, l, s, j,
+                                 stateEnergy, self.alphaC, self.alpha, self.Z, *p, mu)
+        rb = _radial.RadialBatch(np.array([rec]), normalise=True, device=self.device)
+        self.gpu_kernel_launches += rb.kernel_launches
+        return rb.wavefunction(0)
+
+    # --------------------------------------------------------- radial matrix elements
+    @staticmethod
+    def _dipole_allowed(l1, j1, l2, j2):
+        return abs(l1 - l2) == 1 and abs(j1 - j2) < 1.1       # aaf:1016-1019
+
+    @staticmethod
+    def _quadrupole_allowed(l1, j1, l2, j2):
+        dl = abs(l1 - l2)
+        return dl in (0, 1, 2) and abs(j1 - j2) < 2.1           # aaf:1134-1137
+
+    def _ordered_key(self, n1, l1, j1, n2, l2, j2, s=0.5):
+        """lower-energy state first (aaf:1021-1037)."""
+        if self.getEnergy(n1, l1, j1, s=s) > self.getEnergy(n2, l2, j2, s=s):
+            n1, l1, j1, n2, l2, j2 = n2, l2, j2, n1, l1, j1
+        return (round(n1), round(l1), round(2 * j1), round(n2), round(l2), round(2 * j2))
+
+    def precompute_radial(self, dipole_pairs=(), quadrupole_pairs=(), s=0.5,
+                          useLiterature=True):
+        """Evaluate all listed (n1,l1,j1,n2,l2,j2) elements in one GPU batch and memoise
+        them.  This is the batch seam that replaces the reference's sqlite memo
+        (seam B2).  Returns the number of newly computed elements."""
+        todo = []        # (memo dict, key, power)
+        seen = set()
+        for pairs, memo, power, ok in (
+                (dipole_pairs, self._dipole, 1, self._dipole_allowed),
+                (quadrupole_pairs, self._quadrupole, 2, self._quadrupole_allowed)):
+            for (n1, l1, j1, n2, l2, j2) in pairs:
+                if not ok(l1, j1, l2, j2):
+                    continue
+                key = self._ordered_key(n1, l1, j1, n2, l2, j2)
+                if key in memo or (power, key) in seen:
+                    continue
+                if power == 1 and useLiterature and key in self._lit:
+                    continue
+                seen.add((power, key))
+                todo.append((memo, key, power))
+        if not todo:
+            return 0
+        states, index = [], {}
+        pair_rows = np.zeros((len(todo), 3), dtype=np.int32)
+        for t, (memo, key, power) in enumerate(todo):
+            for slot, st in enumerate(((key[0], key[1], key[2] / 2.0),
+                                       (key[3], key[4], key[5] / 2.0))):
+                if st not in index:
+                    index[st] = len(states)
+                    states.append(self._state_record(*st))
+                pair_rows[t, slot] = index[st]
+            pair_rows[t, 2] = power
+        rb = _radial.RadialBatch(np.array(states), normalise=True, device=self.device)
+        vals = rb.integrals(pair_rows)
+        self.gpu_kernel_launches += rb.kernel_launches
+        for (memo, key, power), v in zip(todo, vals):
+            memo[key] = float(v)
+        return len(todo)
+
+    def getRadialMatrixElement(self, n1, l1, j1, n2, l2, j2, s=0.5, useLiterature=True):
+        """Radial dipole element in a0*e (alkali_atom_functions.py:978-1105)."""
+        if not self._dipole_allowed(l1, j1, l2, j2):
+            return 0
+        key = self._ordered_key(n1, l1, j1, n2, l2, j2, s=s)
+        if useLiterature and key in self._lit:
+            return self._lit[key][0]
+        if key not in self._dipole:
+            self.precompute_radial(dipole_pairs=[(n1, l1, j1, n2, l2, j2)],
+                                   useLiterature=False)
+        return self._dipole[key]
+
+    def getQuadrupoleMatrixElement(self, n1, l1, j1, n2, l2, j2, s=0.5):
+        """Radial quadrupole element in a0^2*e (alkali_atom_functions.py:1107-1210)."""
+        if not self._quadrupole_allowed(l1, j1, l2, j2):
+            return 0
+        key = self._ordered_key(n1, l1, j1, n2, l2, j2, s=s)
+        if key not in self._quadrupole:
+            self.precompute_radial(quadrupole_pairs=[(n1, l1, j1, n2, l2, j2)])
+        return self._quadrupole[key]
+
+    def getRadialCoupling(self, n, l, j, n1, l1, j1, s=0.5):
+        """alkali_atom_functions.py:2260-2298."""
+        dl = abs(l - l1)
+        if dl == 1 and abs(j - j1) < 1.1:
+            return self.getRadialMatrixElement(n, l, j, n1, l1, j1, s=s)
+        elif (dl == 0 or dl == 1 or dl == 2) and (abs(j - j1) < 2.1):
+            return self.getQuadrupoleMatrixElement(n, l, j, n1, l1, j1, s=s)
+        return 0
+
+    def updateDipoleMatrixElementsFile(self):
+        """No-op: the memo lives in memory (the reference dumps sqlite -> .npy here,
+        alkali_atom_functions.py:1860-1906)."""
+        return None
+
+    # -------------------------------------------------- angular parts of dipole elements
+    def getReducedMatrixElementL(self, n1, l1, j1, n2, l2, j2, s=0.5):
+        """<l||er||l'> (alkali_atom_functions.py:1277-1309)."""
+        r = self.getRadialMatrixElement(n1, l1, j1, n2, l2, j2, s=s)
+        return (-1) ** l1 * sqrt((2.0 * l1 + 1.0) * (2.0 * l2 + 1.0)) \
+            * _w3j(l1, 1, l2, 0, 0, 0) * r
+
+    def getReducedMatrixElementJ(self, n1, l1, j1, n2, l2, j2, s=0.5):
+        """<j||er||j'> (alkali_atom_functions.py:1311-1345)."""
+        from .wigner import Wigner6j
+        return ((-1) ** (round(l1 + s + j2 + 1.0)) * sqrt((2.0 * j1 + 1.0) * (2.0 * j2 + 1.0))
+                * Wigner6j(j1, 1.0, j2, l2, s, l1)
+                * self.getReducedMatrixElementL(n1, l1, j1, n2, l2, j2, s=s))
+
+    def getDipoleMatrixElement(self, n1, l1, j1, mj1, n2, l2, j2, mj2, q, s=0.5):
+        """<n1 l1 j1 mj1| e r_q |n2 l2 j2 mj2> in a0*e (alkali_atom_functions.py:1347-1401, 2871)."""
+        if abs(q) > 1.1:
+            return 0
+        return ((-1) ** (round(j1 - mj1)) * _w3j(j1, 1, j2, -mj1, -q, mj2)
+                * self.getReducedMatrixElementJ(n1, l1, j1, n2, l2, j2, s=s))
+
+
+def _w3j(*a):
+    from .wigner import Wigner3j
+    try:
+        return Wigner3j(*a)
+    except ValueError:
+        return 0.0
+
+
+class DivalentAtom(AlkaliAtom):
+    """Singlet/triplet series of a divalent atom; radial elements are semiclassical
+    (divalent_atom_functions.py:369-464, 713-783)."""
+
+    divalent = True
+
+    def __init__(self, className, preferQuantumDefects=True, device=None):
+        super().__init__(className, preferQuantumDefects=preferQuantumDefects, device=device)
+        a = self._raw
+        self.defectFittingRange = a["defectFittingRange"]
+        self._savedE = {(r[0], r[1], r[2], r[3]): r[4] for r in a.get("savedEnergy", [])}
+        self._lit = {}
+        for r in a.get("literatureDME", []):
+            key = (r[0], r[1], r[2], r[3], r[4], r[5], r[6])
+            if key not in self._lit or r[8] < self._lit[key][1]:
+                self._lit[key] = (r[7], r[8])
+        self.energyLevelsExtrapolated = False
+
+    def _getSavedEnergy(self, n, l, j, s=0):
+        return self._savedE.get((n, l, float(j), float(s)), 0)
+
+    def getEnergy(self, n, l, j, s=None):
+        """divalent_atom_functions.py:322-353."""
+        if s is None:
+            raise ValueError("Spin state for DivalentAtom has to be explicitly defined "
+                             "as a keyword argument s=0 or s=1")
+        key = (n, l, j, s)
+        if key in self._energy:
+            return self._energy[key]
+        if l >= n:
+            raise ValueError("Requested energy for state l=%d >= n=%d !" % (l, n))
+        stateLabel = "%d%s%d" % (round(2 * s + 1), printStateLetter(l), j)
+        minQuantumDefectN, maxQuantumDefectN = 100000, 0
+        if stateLabel in self.defectFittingRange:
+            minQuantumDefectN, maxQuantumDefectN = self.defectFittingRange[stateLabel]
+        e = None
+        if not self.preferQuantumDefects or n < minQuantumDefectN:
+            savedEnergy = self._getSavedEnergy(n, l, j, s=s)
+            if abs(savedEnergy) > 1e-8:
+                e = savedEnergy
+            elif n < minQuantumDefectN or n > maxQuantumDefectN:
+                self.energyLevelsExtrapolated = True
+        if e is None:
+            defect = self.getQuantumDefect(n, l, j, s=s)
+            e = -self.scaledRydbergConstant / ((n - defect) ** 2)
+        self._energy[key] = e
+        return e
+
+    def radialWavefunction(self, *a, **k):
+        raise NotImplementedError("radialWavefunction calculation for DivalentAtom "
+                                  "has not been implemented yet.")   # div:785-794
+
+    def _ordered(self, n1, l1, j1, n2, l2, j2, s):
+        if self.getEnergy(n1, l1, j1, s=s) > self.getEnergy(n2, l2, j2, s=s):
+            n1, l1, j1, n2, l2, j2 = n2, l2, j2, n1, l1, j1
+        return (round(n1), round(l1), j1, round(n2), round(l2), j2, s)
+
+    def _semiclassical_params(self, key, kind):
+        n1, l1, j1, n2, l2, j2, s = key
+        if kind == 1:   # aaf:2693-2699: nu from energies
+            nu = np.sqrt(-self.scaledRydbergConstant / self.getEnergy(n1, l1, j1, s=s))
+            nu1 = np.sqrt(-self.scaledRydbergConstant / self.getEnergy(n2, l2, j2, s=s))
+        else:           # aaf:2749-2750: nu from quantum defects
+            nu = n1 - self.getQuantumDefect(n1, l1, j1, s=s)
+            nu1 = n2 - self.getQuantumDefect(n2, l2, j2, s=s)
+        return (nu, nu1, l1, l2)
+
+    def precompute_radial(self, dipole_pairs=(), quadrupole_pairs=(), s=None,
+                          useLiterature=True):
+        if s is None:
+            raise ValueError("You must specify total angular momentum s explicitly.")
+        n_new = 0
+        for pairs, memo, kind in ((dipole_pairs, self._dipole, 1),
+                                  (quadrupole_pairs, self._quadrupole, 2)):
+            keys, seen = [], set()
+            for (n1, l1, j1, n2, l2, j2) in pairs:
+                dl = abs(l1 - l2)
+                if kind == 1 and dl != 1:                 # div:404-407 (dj = |j2-j2| == 0)
+                    continue
+                if kind == 2 and not (dl in (0, 1, 2) and abs(j1 - j2) < 2.1):
+                    continue
+                key = self._ordered(n1, l1, j1, n2, l2, j2, s)
+                if key in memo or key in seen:
+                    continue
+                if kind == 1 and useLiterature and key in self._lit:
+                    continue
+                seen.add(key)
+                keys.append(key)
+            if not keys:
+                continue
+            params = np.array([self._semiclassical_params(k, kind) for k in keys])
+            vals = _radial.semiclassical_table(params, kind, device=self.device)
+            self.gpu_kernel_launches += 1
+            for k, v in zip(keys, vals):
+                memo[k] = float(v)
+            n_new += len(keys)
+        return n_new
+
+    def getRadialMatrixElement(self, n1, l1, j1, n2, l2, j2, s=None, useLiterature=True):
+        """divalent_atom_functions.py:369-464."""
+        if s is None:
+            raise ValueError("You must specify total angular momentum s explicitly.")
+        if abs(l1 - l2) != 1:
+            return 0
+        key = self._ordered(n1, l1, j1, n2, l2, j2, s)
+        if useLiterature and key in self._lit:
+            return self._lit[key][0]
+        if key not in self._dipole:
+            self.precompute_radial(dipole_pairs=[(n1, l1, j1, n2, l2, j2)], s=s,
+                                   useLiterature=False)
+        return self._dipole[key]
+
+    def getQuadrupoleMatrixElement(self, n1, l1, j1, n2, l2, j2, s=None):
+        """divalent_atom_functions.py:713-783."""
+        if s is None:
+            raise ValueError("You must specify total angular momentum s explicitly.")
+        dl = abs(l1 - l2)
+        if not (dl in (0, 1, 2) and abs(j1 - j2) < 2.1):
+            return 0
+        key = self._ordered(n1, l1, j1, n2, l2, j2, s)
+        if key not in self._quadrupole:
+            self.precompute_radial(quadrupole_pairs=[(n1, l1, j1, n2, l2, j2)], s=s)
+        return self._quadrupole[key]
+
+
+def _alkali(name):
+    def ctor(preferQuantumDefects=True, cpp_numerov=True, device=None):
+        return AlkaliAtom(name, preferQuantumDefects=preferQuantumDefects,
+                          cpp_numerov=cpp_numerov, device=device)
+    ctor.__name__ = name
+    return ctor
+
+
+def _divalent(name):
+    def ctor(preferQuantumDefects=True, device=None):
+        return DivalentAtom(name, preferQuantumDefects=preferQuantumDefects, device=device)
+    ctor.__name__ = name
+    return ctor
+
+
+Hydrogen = _alkali("Hydrogen")
+Lithium6 = _alkali("Lithium6")
+Lithium7 = _alkali("Lithium7")
+Sodium = _alkali("Sodium")
+Potassium39 = _alkali("Potassium39")
+Potassium = Potassium39
+Potassium40 = _alkali("Potassium40")
+Potassium41 = _alkali("Potassium41")
+Rubidium85 = _alkali("Rubidium85")
+Rubidium = Rubidium85
+Rubidium87 = _alkali("Rubidium87")
+Caesium = _alkali("Caesium")
+Cesium = Caesium
+Strontium88 = _divalent("Strontium88")
+Calcium40 = _divalent("Calcium40")
+Ytterbium174 = _divalent("Ytterbium174")

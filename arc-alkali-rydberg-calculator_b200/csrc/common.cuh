@@ -1,0 +1,44 @@
+// common.cuh -- shared helpers for libarcb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "arcb200.h"
+
+#define ARCB200_FULL_MASK 0xffffffffu
+
+void arcb200_set_error(const char *fmt, ...);
+
+#define ARCB200_CUDA_CHECK(expr)                                                   \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            arcb200_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                              cudaGetErrorString(_e));                             \
+            return -1;                                                             \
+        }                                                                          \
+    } while (0)
+
+#define ARCB200_LAUNCH_CHECK(name)                                                 \
+    do {                                                                           \
+        cudaError_t _e = cudaGetLastError();                                       \
+        if (_e != cudaSuccess) {                                                   \
+            arcb200_set_error("launch of %s failed: %s", name,                     \
+                              cudaGetErrorString(_e));                             \
+            return -2;                                                             \
+        }                                                                          \
+    } while (0)
+
+static __device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ARCB200_FULL_MASK, v, o);
+    return v;
+}
+
+static __device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(ARCB200_FULL_MASK, v, o));
+    return v;
+}

@@ -1,0 +1,120 @@
+"""Host side of subsystem (1): batches radial states / pairs for the CUDA kernels.
+
+`RadialBatch` packs a set of radial states into `arcb200_state_t` records, runs the
+batched Numerov kernel (one warp per state) and keeps the wavefunctions RESIDENT in
+HBM; radial dipole/quadrupole integrals for any list of state pairs are then one
+more kernel launch (one warp per pair).  Replaces the per-element call chain
+getRadialMatrixElement -> radialWavefunction x2 -> NumerovWavefunction -> trapezoid
+(alkali_atom_functions.py:978-1105, 503-625) of the reference.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def make_state(innerLimit, outerLimit, step, init1, init2, l, s, j, stateEnergy,
+               alphaC, alpha, Z, a1, a2, a3, a4, rc, mu):
+    """One arcb200_state_t record from the reference's 18 C-extension arguments
+    (arc_c_extensions.c:113-116)."""
+    rec = np.zeros((), dtype=_lib.STATE_DTYPE)
+    rec["innerLimit"], rec["outerLimit"], rec["step"] = innerLimit, outerLimit, step
+    rec["init1"], rec["init2"] = init1, init2
+    rec["l"], rec["s"], rec["j"], rec["stateEnergy"] = int(l), s, j, stateEnergy
+    rec["alphaC"], rec["alpha"], rec["Z"] = alphaC, alpha, int(Z)
+    rec["a1"], rec["a2"], rec["a3"], rec["a4"], rec["rc"], rec["mu"] = a1, a2, a3, a4, rc, mu
+    return rec
+
+
+class RadialBatch:
+    """Wavefunctions of `states` (structured array of arcb200_state_t) on the GPU."""
+
+    def __init__(self, states, normalise=True, device=None):
+        import torch
+        lib = _lib.load()
+        self.device = _lib.require_device(device)
+        self.states = np.ascontiguousarray(states, dtype=_lib.STATE_DTYPE).reshape(-1)
+        n = self.n = len(self.states)
+        self.offsets = np.zeros(n + 1, dtype=np.int64)
+        total = lib.arcb200_numerov_lengths(n, self.states.ctypes.data,
+                                            self.offsets.ctypes.data)
+        _lib.check(total, "arcb200_numerov_lengths")
+        self.total = int(total)
+        self.lengths = self.states["length"].copy()
+        dev = torch.device("cuda", self.device)
+        order = np.argsort(-self.lengths, kind="stable").astype(np.int32)
+        self.d_states = torch.from_numpy(self.states.view(np.uint8).copy()).to(dev)
+        self.d_offsets = torch.from_numpy(self.offsets).to(dev)
+        self.d_order = torch.from_numpy(order).to(dev)
+        self.d_psi = torch.empty(self.total + 64, dtype=torch.float64, device=dev)
+        self.d_r = torch.empty(self.total + 64, dtype=torch.float64, device=dev)
+        self.d_norm = torch.empty(n, dtype=torch.float64, device=dev)
+        self.d_dp = torch.empty(n, dtype=torch.int32, device=dev)
+        rc = lib.arcb200_numerov_batch(
+            self.device, _lib.stream_ptr(self.device), n, _lib.ptr(self.d_states),
+            _lib.ptr(self.d_offsets), _lib.ptr(self.d_order), _lib.ptr(self.d_psi),
+            _lib.ptr(self.d_r), _lib.ptr(self.d_norm), _lib.ptr(self.d_dp),
+            1 if normalise else 0)
+        _lib.check(rc, "arcb200_numerov_batch")
+        self.kernel_launches = 1
+
+    def wavefunction(self, i):
+        """(r, psi) of state i as numpy arrays (device -> host copy)."""
+        o, L = int(self.offsets[i]), int(self.lengths[i])
+        return (self.d_r[o:o + L].cpu().numpy(), self.d_psi[o:o + L].cpu().numpy())
+
+    def divergence_points(self):
+        return self.d_dp.cpu().numpy()
+
+    def norms(self):
+        return self.d_norm.cpu().numpy()
+
+    def integrals_device(self, pairs):
+        """pairs: int32[npairs,3] = (state a (lower energy), state b, power). Returns a
+        CUDA float64 tensor of trapezoid(psi_a psi_b r_a^power, r_a)[0:min(La,Lb)]."""
+        import torch
+        lib = _lib.load()
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
+        dev = torch.device("cuda", self.device)
+        d_pairs = torch.from_numpy(pairs).to(dev)
+        out = torch.empty(len(pairs), dtype=torch.float64, device=dev)
+        rc = lib.arcb200_radial_integrals(
+            self.device, _lib.stream_ptr(self.device), len(pairs), _lib.ptr(d_pairs),
+            _lib.ptr(self.d_states), _lib.ptr(self.d_offsets), _lib.ptr(self.d_psi),
+            _lib.ptr(self.d_r), _lib.ptr(out))
+        _lib.check(rc, "arcb200_radial_integrals")
+        self.kernel_launches += 1
+        return out
+
+    def integrals(self, pairs):
+        return self.integrals_device(pairs).cpu().numpy()
+
+
+_GL_CACHE = {}
+
+
+def semiclassical_table(params, kind, device=None, nq=256):
+    """params: float64[n,4] = (nu, nu1, l1, l2) -> semiclassical radial elements
+    (alkali_atom_functions.py:2683-2802) evaluated on the GPU."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    if len(params) == 0:
+        return np.zeros(0)
+    dn = np.abs(params[:, 0] - params[:, 1]).max()
+    while nq < 2.0 * dn + 64:
+        nq *= 2
+    if nq not in _GL_CACHE:
+        x, w = np.polynomial.legendre.leggauss(nq)
+        _GL_CACHE[nq] = np.concatenate([x, w])
+    dev = torch.device("cuda", device)
+    d_in = torch.from_numpy(params).to(dev)
+    d_q = torch.from_numpy(_GL_CACHE[nq]).to(dev)
+    out = torch.empty(len(params), dtype=torch.float64, device=dev)
+    rc = lib.arcb200_semiclassical_table(device, _lib.stream_ptr(device), len(params),
+                                         _lib.ptr(d_in), int(kind), _lib.ptr(d_q), nq,
+                                         _lib.ptr(out))
+    _lib.check(rc, "arcb200_semiclassical_table")
+    return out.cpu().numpy()

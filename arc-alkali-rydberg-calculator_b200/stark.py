@@ -1,0 +1,231 @@
+"""StarkMap -- drop-in for arc.calculations_atom_single.StarkMap on the hot path.
+
+Same constructor, `defineBasis` and `diagonalise` signatures and result attributes
+as the reference (calculations_atom_single.py:494-1025); the radial table comes from
+the batched CUDA Numerov kernels and the per-field eigensolves from the batched CUDA
+eigensolver (sweep.stark_sweep).  No CPU fallback.
+"""
+import numpy as np
+from scipy.constants import physical_constants, h as C_h, e as C_e
+
+from .wigner import CG
+from . import sweep as _sweep
+
+
+class CompositionView:
+    """Lazy list-of-lists view of the top-k composition arrays.
+
+    `composition[f][i]` -> list of [coefficient, basis index] pairs, the layout of
+    the reference's `_stateComposition2` (calculations_atom_single.py:1395-1416),
+    materialised on access so a 600 x 410 x 3 sweep does not cost 700k Python lists.
+    """
+
+    def __init__(self, comp_c, comp_i):
+        self.comp_c, self.comp_i = comp_c, comp_i
+
+    def __len__(self):
+        return self.comp_c.shape[0]
+
+    def __getitem__(self, f):
+        if isinstance(f, slice):
+            return [self[k] for k in range(*f.indices(len(self)))]
+        c, i = self.comp_c[f], self.comp_i[f]
+        return [[[c[a, b], int(i[a, b])] for b in range(c.shape[1]) if i[a, b] >= 0]
+                for a in range(c.shape[0])]
+
+    def __iter__(self):
+        for f in range(len(self)):
+            yield self[f]
+
+
+def efield_angular(l1, j1, mj1, l2, j2, mj2, s=0.5):
+    """sum_ml CG CG sqrt((l>^2-ml^2)/((2l>+1)(2l>-1)))  (PRA 20, 2251 eq. 10;
+    alkali_atom_functions.py:4513-4553 `_EFieldCoupling.getAngular`)."""
+    sumPart = 0.0
+    for ml in np.linspace(mj1 - s, mj1 + s, round(2 * s + 1)):
+        if (abs(ml) - 0.1 < l1) and (abs(ml) - 0.1 < l2):
+            angularPart = 0.0
+            if abs(l1 - l2 - 1) < 0.1:
+                angularPart = ((l1 ** 2 - ml ** 2) / ((2.0 * l1 + 1.0) * (2.0 * l1 - 1.0))) ** 0.5
+            elif abs(l1 - l2 + 1) < 0.1:
+                angularPart = ((l2 ** 2 - ml ** 2) / ((2.0 * l2 + 1.0) * (2.0 * l2 - 1.0))) ** 0.5
+            sumPart += (CG(l1, ml, s, mj1 - ml, j1, mj1) * CG(l2, ml, s, mj1 - ml, j2, mj2)
+                        * angularPart)
+    return sumPart
+
+
+class StarkMap:
+    """Stark maps: basis |n l j mj>, H(F) = mat1 + F * mat2, eigensolve per field."""
+
+    def __init__(self, atom):
+        self.atom = atom
+        self.basisStates = []
+        self.mat1 = []
+        self.mat2 = []
+        self.indexOfCoupledState = 0
+        self.eFieldList = []
+        self.y = []
+        self.highlight = []
+        self.composition = []
+        self.fig = 0
+        self.ax = 0
+        self.fitX, self.fitY, self.fittedCurveY = [], [], []
+        self.drivingFromState = [0, 0, 0, 0, 0]
+        self.maxCoupling = 0.0
+        self.eFieldCouplingSaved = False
+        self.s = 0.5
+        self.gpu_kernel_launches = 0
+        self.last_sweep = None
+
+    def _eFieldCouplingDivE(self, n1, l1, j1, mj1, n2, l2, j2, mj2, s=0.5):
+        """calculations_atom_single.py:650-666."""
+        if (abs(mj1 - mj2) > 0.1) or (abs(l1 - l2) != 1):
+            return 0
+        result = (self.atom.getRadialMatrixElement(n1, l1, j1, n2, l2, j2, s=s)
+                  * physical_constants["Bohr radius"][0] * C_e)
+        return result * efield_angular(l1, j1, mj1, l2, j2, mj2, s=s)
+
+    def defineBasis(self, n, l, j, mj, nMin, nMax, maxL, Bz=0, progressOutput=False,
+                    debugOutput=False, s=0.5):
+        """calculations_atom_single.py:674-844 -- same basis order, `mat1` (GHz) and
+        `mat2` (GHz/(V/m)) dense float64; all radial elements in one GPU batch."""
+        self.n, self.l, self.j, self.mj = n, l, j, mj
+        self.nMin, self.nMax, self.maxL, self.Bz, self.s = nMin, nMax, maxL, Bz, s
+        states = []
+        for tn in range(nMin, nMax + 1):
+            for tl in range(min(maxL + 1, tn)):
+                for tj in np.linspace(tl - s, tl + s, round(2 * s + 1)):
+                    if (abs(mj) - 0.1 <= tj) and (tn >= self.atom.groundStateN
+                                                  or [tn, tl, tj] in self.atom.extraLevels):
+                        states.append([tn, tl, tj, mj])
+        dimension = len(states)
+        if progressOutput:
+            print("Found ", dimension, " states.")
+        indexOfCoupledState = 0
+        for index, st in enumerate(states):
+            if (st[0] == n) and (abs(st[1] - l) < 0.1) and (abs(st[2] - j) < 0.1) \
+                    and (abs(st[3] - mj) < 0.1):
+                indexOfCoupledState = index
+        self.basisStates = states
+        self.indexOfCoupledState = indexOfCoupledState
+
+        # --- batch seam: every |dl|=1 pair goes to the GPU radial table at once
+        by_l = {}
+        for idx, st in enumerate(states):
+            by_l.setdefault(st[1], []).append(idx)
+        pairs = []
+        for l1, idxs in by_l.items():
+            for idx2 in by_l.get(l1 + 1, []):
+                for idx1 in idxs:
+                    pairs.append((idx1, idx2))
+        before = self.atom.gpu_kernel_launches
+        want = [(states[a][0], states[a][1], states[a][2],
+                 states[b][0], states[b][1], states[b][2]) for a, b in pairs]
+        if getattr(self.atom, "divalent", False):
+            self.atom.precompute_radial(dipole_pairs=want, s=s)
+        else:
+            self.atom.precompute_radial(dipole_pairs=want)
+        self.gpu_kernel_launches += self.atom.gpu_kernel_launches - before
+
+        mat1 = np.zeros((dimension, dimension), dtype=np.double)
+        mat2 = np.zeros((dimension, dimension), dtype=np.double)
+        for ii in range(dimension):
+            mat1[ii][ii] = (self.atom.getEnergy(states[ii][0], states[ii][1], states[ii][2],
+                                                s=self.s) * C_e / C_h * 1e-9
+                            + self.atom.getZeemanEnergyShift(states[ii][1], states[ii][2],
+                                                             states[ii][3], self.Bz, s=self.s)
+                            / C_h * 1.0e-9)
+        ang = {}
+        for a, b in pairs:
+            ii, jj = (a, b) if a < b else (b, a)
+            k = (states[ii][1], states[ii][2], states[jj][1], states[jj][2])
+            if k not in ang:
+                ang[k] = efield_angular(states[ii][1], states[ii][2], mj,
+                                        states[jj][1], states[jj][2], mj, s=self.s)
+            coupling = (self.atom.getRadialMatrixElement(
+                states[ii][0], states[ii][1], states[ii][2],
+                states[jj][0], states[jj][1], states[jj][2], s=self.s)
+                * physical_constants["Bohr radius"][0] * C_e * ang[k]) * 1.0e-9 / C_h
+            mat2[jj][ii] = coupling
+            mat2[ii][jj] = coupling
+        self.mat1, self.mat2 = mat1, mat2
+        return 0
+
+    def diagonalise(self, eFieldList, drivingFromState=[0, 0, 0, 0, 0], progressOutput=False,
+                    debugOutput=False, upTo=4, totalContributionMax=0.95, batch=None):
+        """calculations_atom_single.py:846-1025.  Results: `y` (list of ascending
+        eigenvalue arrays, GHz), `highlight`, `composition` -- same indexing as the
+        reference; eigenvectors never leave the GPU."""
+        dimension = len(self.basisStates)
+        self.maxCoupling = 0.0
+        self.drivingFromState = drivingFromState
+        drive_w = None
+        if self.drivingFromState[0] != 0:
+            n1, l1 = round(drivingFromState[0]), round(drivingFromState[1])
+            j1, m1, q = drivingFromState[2], drivingFromState[3], drivingFromState[4]
+            coupling = []
+            for i in range(dimension):
+                thisCoupling = 0.0
+                b = self.basisStates[i]
+                if (round(abs(b[1] - l1)) == 1) and (round(abs(b[2] - j1)) <= 1) \
+                        and (round(abs(b[3] - m1 - q)) == 0):
+                    thisCoupling += self.atom.getDipoleMatrixElement(
+                        n1, l1, j1, m1, round(b[0]), round(b[1]), b[2], b[3], q, s=self.s)
+                thisCoupling = abs(thisCoupling) ** 2
+                self.maxCoupling = max(self.maxCoupling, thisCoupling)
+                coupling.append(thisCoupling)
+            if self.maxCoupling < 0.00000001:
+                raise Exception(
+                    "State that you specified in drivingFromState, for a given laser "
+                    "polarization, is uncoupled from the specified Stark manifold.")
+            drive_w = np.abs(np.array(coupling) / self.maxCoupling)   # single:1009-1011
+        self.eFieldList = eFieldList
+        fields = np.asarray(eFieldList, dtype=np.float64)
+        topk = dimension if upTo == -1 else max(upTo - 1, 0)
+        cmax = 2.0 if upTo == -1 else totalContributionMax
+        res = _sweep.stark_sweep(np.diag(self.mat1).copy(), self.mat2, fields,
+                                 self.indexOfCoupledState, drive_w=drive_w, topk=topk,
+                                 contrib_max=cmax, device=getattr(self.atom, "device", None),
+                                 batch=batch)
+        self.last_sweep = res
+        self.gpu_kernel_launches += res.kernel_launches
+        self.y = [res.y[f] for f in range(len(fields))]
+        self.highlight = [res.hl[f] for f in range(len(fields))]
+        self.composition = CompositionView(res.comp_c, res.comp_i)
+        return
+
+    def getPolarizability(self, maxField=1.0e10, showPlot=False, debugOutput=False,
+                          minStateContribution=0.0):
+        """calculations_atom_single.py:1432-1575 (fit of the tracked level to
+        offset - alpha F^2 / 2); returns MHz cm^2 / V^2."""
+        from scipy.optimize import curve_fit
+        if self.drivingFromState[0] != 0:
+            raise Exception("Program can only find Polarizability of the original state "
+                            "if you highlight original state.")
+        eFieldList = np.asarray(self.eFieldList)
+        hl = np.asarray(self.highlight)
+        y = np.asarray(self.y)
+        st = self.basisStates[self.indexOfCoupledState]
+        e0 = self.atom.getEnergy(st[0], st[1], st[2], s=self.s) * C_e / C_h * 1e-9
+        stop = 0
+        while stop < len(eFieldList) - 1 and eFieldList[stop] < maxField:
+            stop += 1
+        xs, ys = [], []
+        for ii in range(stop):
+            jj = int(np.argmax(hl[ii]))
+            if minStateContribution < hl[ii][jj]:
+                xs.append(eFieldList[ii])
+                ys.append(y[ii][jj] - e0)
+        xs = np.array(xs) / 100.0
+        ys = np.array(ys)
+
+        def polarizabilityFit(eField, offset, alpha):
+            return offset - 0.5 * alpha * eField ** 2
+        try:
+            popt, _ = curve_fit(polarizabilityFit, xs, ys, [0, 0])
+        except Exception as ex:
+            print(ex)
+            return 0
+        self.fitX, self.fitY = xs, ys
+        self.fittedCurveY = np.array([polarizabilityFit(v, popt[0], popt[1]) for v in xs])
+        return popt[1] * 1.0e3

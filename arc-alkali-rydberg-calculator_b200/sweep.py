@@ -1,0 +1,215 @@
+"""Sweep driver: Hamiltonian assembly + batched eigensolve over field / distance points.
+
+Host side of subsystems (2)+(3).  Sweep points are independent eigenproblems that
+share H0 and V (or matDiagonal and matR), so they shard with NO data-path
+collective: rank g of G takes the contiguous slice points[g*P/G:(g+1)*P/G]
+(SURVEY.md 8e), solves it on its own GPU, and the per-rank results are
+all-gathered once at the end (NCCL on GPUs; gloo in the CPU tests).
+"""
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(npoints, rank, world):
+    """Contiguous slice [lo, hi) of `npoints` sweep points owned by `rank`."""
+    lo = (npoints * rank) // world
+    hi = (npoints * (rank + 1)) // world
+    return lo, hi
+
+
+def dist_info(group=None):
+    """(rank, world) of the default process group, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(group), dist.get_world_size(group)
+    except Exception:
+        pass
+    return 0, 1
+
+
+def gather_rows(local, npoints, group=None):
+    """All-gather per-rank row blocks (torch tensors, first dim = local points) into the
+    full [npoints, ...] tensor on every rank.  Ragged shards are padded to the largest."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(npoints, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
+
+
+def _pick_batch(N, npoints, nvec, device, batch=None):
+    import torch
+    if batch is not None:
+        return max(1, min(int(batch), npoints))
+    free, _total = torch.cuda.mem_get_info(device)
+    lib = _lib.load()
+    per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
+    b = int(min(npoints, max(1, (0.6 * free) // per)))
+    # two waves of one cluster-per-matrix tridiagonalisation keep 148 SMs busy
+    cap = 592 if N <= 512 else (148 if N <= 1024 else (72 if N <= 4096 else 18))
+    return max(1, min(b, cap))
+
+
+class SweepResult:
+    __slots__ = ("y", "hl", "comp_c", "comp_i", "kernel_launches", "h2d_bytes", "d2h_bytes")
+
+
+def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
+                device=None, batch=None, distributed=True, to_host=True):
+    """Solve H = diag(h0) + F*V for every F (calculations_atom_single.py:976-1021)."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    fields = np.ascontiguousarray(fields, dtype=np.float64)
+    nF_all = len(fields)
+    rank, world = dist_info() if distributed else (0, 1)
+    lo, hi = shard_bounds(nF_all, rank, world)
+    nF = hi - lo
+    N = int(len(h0diag))
+    res = SweepResult()
+    d_h0 = torch.as_tensor(np.ascontiguousarray(h0diag, dtype=np.float64)).to(dev, non_blocking=True)
+    d_V = torch.as_tensor(np.ascontiguousarray(V, dtype=np.float64)).to(dev, non_blocking=True)
+    d_F = torch.as_tensor(fields[lo:hi].copy()).to(dev, non_blocking=True)
+    d_w = None
+    if drive_w is not None:
+        d_w = torch.as_tensor(np.ascontiguousarray(drive_w, dtype=np.float64)).to(dev)
+    res.h2d_bytes = (d_h0.numel() + d_V.numel() + d_F.numel()) * 8
+    y = torch.empty((nF, N), dtype=torch.float64, device=dev)
+    hl = torch.empty((nF, N), dtype=torch.float64, device=dev)
+    comp_c = torch.zeros((nF, N, max(topk, 1)), dtype=torch.float64, device=dev)
+    comp_i = torch.full((nF, N, max(topk, 1)), -1, dtype=torch.int32, device=dev)
+    if nF > 0:
+        b = _pick_batch(N, nF, N, device, batch)
+        wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, N))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        rc = lib.arcb200_stark_sweep(device, _lib.stream_ptr(device), N, _lib.ptr(d_h0),
+                                     _lib.ptr(d_V), nF, _lib.ptr(d_F), int(idx0),
+                                     _lib.ptr(d_w), int(topk), float(contrib_max),
+                                     _lib.ptr(y), _lib.ptr(hl), _lib.ptr(comp_c),
+                                     _lib.ptr(comp_i), _lib.ptr(work), wbytes, b)
+        _lib.check(rc, "arcb200_stark_sweep")
+        res.kernel_launches = rc
+    else:
+        res.kernel_launches = 0
+    if world > 1:
+        y, hl = gather_rows(y, nF_all), gather_rows(hl, nF_all)
+        comp_c, comp_i = gather_rows(comp_c, nF_all), gather_rows(comp_i, nF_all)
+    if to_host:
+        res.y, res.hl = y.cpu().numpy(), hl.cpu().numpy()
+        res.comp_c, res.comp_i = comp_c.cpu().numpy(), comp_i.cpu().numpy()
+        res.d2h_bytes = res.y.nbytes + res.hl.nbytes + res.comp_c.nbytes + res.comp_i.nbytes
+    else:
+        res.y, res.hl, res.comp_c, res.comp_i = y, hl, comp_c, comp_i
+        res.d2h_bytes = 0
+    return res
+
+
+class PairOperators:
+    """matDiagonal + dense matR[o] staged once on the device (scatter of the COO
+    entries; the reference keeps scipy CSR, calculations_atom_pairstate.py:3222-3239)."""
+
+    def __init__(self, h0diag, matR_coo, N, device=None):
+        import torch
+        lib = _lib.load()
+        self.device = _lib.require_device(device)
+        dev = torch.device("cuda", self.device)
+        self.N = int(N)
+        self.d_h0 = torch.as_tensor(np.ascontiguousarray(h0diag, dtype=np.float64)).to(dev)
+        self.d_M = []
+        self.h2d_bytes = self.d_h0.numel() * 8
+        for rows, cols, vals in matR_coo:
+            rows = torch.as_tensor(np.ascontiguousarray(rows, dtype=np.int32)).to(dev)
+            cols = torch.as_tensor(np.ascontiguousarray(cols, dtype=np.int32)).to(dev)
+            vals = torch.as_tensor(np.ascontiguousarray(vals, dtype=np.float64)).to(dev)
+            self.h2d_bytes += rows.numel() * 4 + cols.numel() * 4 + vals.numel() * 8
+            dense = torch.zeros((self.N, self.N), dtype=torch.float64, device=dev)
+            if vals.numel():
+                rc = lib.arcb200_scatter_coo(self.device, _lib.stream_ptr(self.device),
+                                             self.N, vals.numel(), _lib.ptr(rows),
+                                             _lib.ptr(cols), _lib.ptr(vals), _lib.ptr(dense))
+                _lib.check(rc, "arcb200_scatter_coo")
+            self.d_M.append(dense)
+        self.d_Mptrs = torch.tensor([int(m.data_ptr()) for m in self.d_M],
+                                    dtype=torch.int64, device=dev)
+
+
+def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, batch=None,
+               distributed=True, to_host=True):
+    """k eigenpairs nearest sigma of H(R) for every R (already sorted by the caller,
+    calculations_atom_pairstate.py:3307, 3425-3520)."""
+    import torch
+    lib = _lib.load()
+    device = ops.device
+    dev = torch.device("cuda", device)
+    rangeR = np.ascontiguousarray(rangeR, dtype=np.float64)
+    nR_all = len(rangeR)
+    rank, world = dist_info() if distributed else (0, 1)
+    lo, hi = shard_bounds(nR_all, rank, world)
+    nR = hi - lo
+    N = ops.N
+    res = SweepResult()
+    d_R = torch.as_tensor(rangeR[lo:hi].copy()).to(dev)
+    d_w = None
+    if drive_w is not None:
+        d_w = torch.as_tensor(np.ascontiguousarray(drive_w, dtype=np.float64)).to(dev)
+    res.h2d_bytes = ops.h2d_bytes + d_R.numel() * 8
+    y = torch.empty((nR, k), dtype=torch.float64, device=dev)
+    hl = torch.empty((nR, k), dtype=torch.float64, device=dev)
+    comp_c = torch.zeros((nR, k, max(topk, 1)), dtype=torch.float64, device=dev)
+    comp_i = torch.full((nR, k, max(topk, 1)), -1, dtype=torch.int32, device=dev)
+    if nR > 0:
+        b = _pick_batch(N, nR, k, device, batch)
+        wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, k))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        rc = lib.arcb200_pair_sweep(device, _lib.stream_ptr(device), N, _lib.ptr(ops.d_h0),
+                                    len(ops.d_M), _lib.ptr(ops.d_Mptrs), nR, _lib.ptr(d_R),
+                                    int(k), float(sigma_ghz), int(opi), _lib.ptr(d_w),
+                                    int(topk), _lib.ptr(y), _lib.ptr(hl), _lib.ptr(comp_c),
+                                    _lib.ptr(comp_i), _lib.ptr(work), wbytes, b)
+        _lib.check(rc, "arcb200_pair_sweep")
+        res.kernel_launches = rc
+    else:
+        res.kernel_launches = 0
+    if world > 1:
+        y, hl = gather_rows(y, nR_all), gather_rows(hl, nR_all)
+        comp_c, comp_i = gather_rows(comp_c, nR_all), gather_rows(comp_i, nR_all)
+    if to_host:
+        res.y, res.hl = y.cpu().numpy(), hl.cpu().numpy()
+        res.comp_c, res.comp_i = comp_c.cpu().numpy(), comp_i.cpu().numpy()
+        res.d2h_bytes = res.y.nbytes + res.hl.nbytes + res.comp_c.nbytes + res.comp_i.nbytes
+    else:
+        res.y, res.hl, res.comp_c, res.comp_i = y, hl, comp_c, comp_i
+        res.d2h_bytes = 0
+    return res
+
+
+def syevd_batched(A, device=None):
+    """numpy.linalg.eigh replacement for a stack of symmetric matrices [batch,N,N].
+    Returns (w[batch,N] ascending, v[batch,N,N] with v[b][:, i] the i-th eigenvector)."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[None]
+    batch, N, _ = A.shape
+    d_A = torch.as_tensor(A).to(dev)
+    d_w = torch.empty((batch, N), dtype=torch.float64, device=dev)
+    d_Z = torch.empty((batch, N, N), dtype=torch.float64, device=dev)
+    wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rc = lib.arcb200_syevd_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
+                                   _lib.ptr(d_w), _lib.ptr(d_Z), _lib.ptr(work), wbytes)
+    _lib.check(rc, "arcb200_syevd_batched")
+    return d_w.cpu().numpy(), np.ascontiguousarray(d_Z.cpu().numpy().transpose(0, 2, 1))

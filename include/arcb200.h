@@ -1,0 +1,149 @@
+/*
+ * include/arcb200.h -- C-ABI of libarcb200.so, the B200 (sm_100a) hot path of ARC.
+ *
+ * Plain pointers and sizes only; no torch / CPython types.  Every entry point
+ * names the reference interface (file:line under /root/reference) it replaces.
+ * Conventions:
+ *   - every `d_*` pointer is DEVICE memory owned by the caller (the Python host
+ *     passes torch CUDA tensors' data_ptr()); the library never allocates
+ *     result buffers and never frees caller memory;
+ *   - `device` is the CUDA ordinal, `stream` a cudaStream_t passed as void*
+ *     (NULL = legacy default stream);
+ *   - return value 0 = success, negative = error; arcb200_last_error() returns a
+ *     thread-local message.  Nothing calls exit()/abort() (the reference's C
+ *     extension returns NULL without setting an exception, arc_c_extensions.c:145,200);
+ *   - re-entrant per (device, stream); no file-scope state (the reference keeps all
+ *     integrator state in globals, arc_c_extensions.c:11-24,57-67).
+ */
+#ifndef ARCB200_H
+#define ARCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARCB200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------ */
+/* library                                                                   */
+/* ------------------------------------------------------------------------ */
+int arcb200_abi_version(void);
+const char *arcb200_last_error(void);
+/* fills props[0..7] = {sm_count, cc_major, cc_minor, l2_bytes, smem_per_block_optin,
+ *                      total_mem_MiB, cluster_launch_supported, clock_khz} */
+int arcb200_device_info(int device, int64_t *props);
+
+/* ------------------------------------------------------------------------ */
+/* subsystem (1): Numerov radial wavefunctions + radial integrals            */
+/* ------------------------------------------------------------------------ */
+
+/* One radial state = the 18 scalars of the reference's C-extension call
+ * NumerovWavefunction(innerLimit, outerLimit, step, init1, init2, l, s, j,
+ *   stateEnergy, alphaC, alpha, Z, a1, a2, a3, a4, rc, mu)
+ * (arc_c_extensions.c:113-116, format "dddddidddddidddddd"). 144 bytes. */
+typedef struct arcb200_state {
+    double innerLimit, outerLimit, step, init1, init2;
+    double s, j, stateEnergy, alphaC, alpha;
+    double a1, a2, a3, a4, rc, mu;
+    int32_t l, Z;
+    int32_t length;   /* filled by arcb200_numerov_lengths: grid points L */
+    int32_t _pad;
+} arcb200_state_t;
+
+/* L = (int)((sqrt(outer)-sqrt(inner))/step)  (arc_c_extensions.c:131).
+ * Host-side, fills states[i].length and offsets[0..n] (prefix sum, each segment
+ * padded to a multiple of 32 doubles); returns total doubles needed, <0 on error. */
+int64_t arcb200_numerov_lengths(int32_t nstates, arcb200_state_t *h_states,
+                                int64_t *h_offsets);
+
+/* Batched replacement of NumerovWavefunction (arc_c_extensions.c:108-285) fused with
+ * the normalisation of AlkaliAtom.radialWavefunction (alkali_atom_functions.py:603-606).
+ * One warp per state.  Outputs, per state i at [d_offsets[i], d_offsets[i]+length):
+ *   d_psi  = R(r)*r   (normalised so trapezoid(psi^2, r) = 1 if normalise!=0,
+ *                      else raw like the C extension's row 0), zero below the
+ *                      divergence point
+ *   d_r    = r grid   (the C extension's row 1)
+ *   d_norm[i] = trapezoid(psi_raw^2, r);  d_dp[i] = divergencePoint
+ * d_order = processing order (state indices, longest first) or NULL. */
+int arcb200_numerov_batch(int device, void *stream, int32_t nstates,
+                          const arcb200_state_t *d_states, const int64_t *d_offsets,
+                          const int32_t *d_order, double *d_psi, double *d_r,
+                          double *d_norm, int32_t *d_dp, int32_t normalise);
+
+/* Batched radial overlap integrals, one warp per pair:
+ *   out[p] = trapezoid(psi_a*psi_b*r_a^power, x=r_a)[0:min(La,Lb)]
+ * replaces the integration in AlkaliAtom.getRadialMatrixElement
+ * (alkali_atom_functions.py:1087-1096, power=1) and getQuadrupoleMatrixElement
+ * (alkali_atom_functions.py:1191-1201, power=2).  d_pairs = int32[npairs][3] =
+ * {state a (lower energy; its r grid is used), state b, power}. */
+int arcb200_radial_integrals(int device, void *stream, int64_t npairs,
+                             const int32_t *d_pairs, const arcb200_state_t *d_states,
+                             const int64_t *d_offsets, const double *d_psi,
+                             const double *d_r, double *d_out);
+
+/* Semiclassical radial elements used by all divalent atoms
+ * (alkali_atom_functions.py:2683-2735 dipole, 2737-2802 quadrupole; the Anger
+ * functions J_{dnu-+1}(-dnu) replace mpmath.angerj).  One warp per element.
+ * d_in = double[n][4] = {nu (state 1), nu1 (state 2), l1, l2}; kind 1|2;
+ * d_quad = double[2][nq]: Gauss-Legendre nodes then weights on [-1,1], nq % 32 == 0. */
+int arcb200_semiclassical_table(int device, void *stream, int64_t n,
+                                const double *d_in, int32_t kind,
+                                const double *d_quad, int32_t nq, double *d_out);
+
+/* ------------------------------------------------------------------------ */
+/* subsystems (2)+(3): Hamiltonian assembly + batched symmetric eigensolve   */
+/* ------------------------------------------------------------------------ */
+
+/* Workspace size (bytes) for a sweep of `batch` matrices of order N solved
+ * concurrently with nvec eigenvectors kept (nvec = N for Stark maps). */
+int64_t arcb200_sweep_workspace_bytes(int32_t N, int32_t batch, int32_t nvec);
+
+/* Stark-map sweep: for every field F[f]:  H = diag(h0) + F[f]*V   (dense, FP64),
+ * full symmetric eigendecomposition, then
+ *   y[f][i]  = eigenvalue i (ascending)
+ *   hl[f][i] = |v[idx0,i]|^2                 if d_drive_w == NULL
+ *            = sum_j drive_w[j] |v[j,i]|^2   otherwise
+ *   comp_c/comp_i[f][i][0..topk) = coefficient/index of the largest |v[:,i]|
+ *            entries, descending, stopping once sum c^2 >= contrib_max
+ *            (unused slots: index -1)
+ * Replaces the loop body of StarkMap.diagonalise
+ * (calculations_atom_single.py:976-1021, _stateComposition2 1395-1416,
+ *  numpy.linalg.eigh at 986). */
+int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
+                        const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
+                        const double *d_drive_w, int32_t topk, double contrib_max,
+                        double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
+                        void *d_work, int64_t work_bytes, int32_t batch);
+
+/* Pair-state sweep: for every distance R[p] (micrometres):
+ *   H = diag(h0) + sum_o M_o / (R*1e-6)^(3+o)      (M_o dense N x N, o < norders)
+ * k eigenpairs nearest sigma (GHz), ascending; hl/comp as above (topk entries).
+ * Replaces the loop body of PairStateInteractions.diagonalise
+ * (calculations_atom_pairstate.py:3425-3520; scipy eigsh at 3444-3450). */
+int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
+                       int32_t norders, const double *const *d_M, int32_t nR,
+                       const double *d_R, int32_t k, double sigma, int32_t opi,
+                       const double *d_drive_w, int32_t topk, double *d_y, double *d_hl,
+                       double *d_comp_c, int32_t *d_comp_i, void *d_work,
+                       int64_t work_bytes, int32_t batch);
+
+/* Sparse (COO) -> dense scatter used to stage matR[o] on the device
+ * (the reference keeps matR as scipy CSR, calculations_atom_pairstate.py:3230-3239). */
+int arcb200_scatter_coo(int device, void *stream, int32_t N, int64_t nnz,
+                        const int32_t *d_rows, const int32_t *d_cols,
+                        const double *d_vals, double *d_dense);
+
+/* Batched dense symmetric eigensolver on caller-assembled matrices
+ * (d_A: batch x N x N, overwritten).  Exposed for tests and for callers with
+ * other Hamiltonians (numpy.linalg.eigh replacement, calculations_atom_single.py:986).
+ * d_w: batch x N ascending; d_Z: batch x N x N, eigenvector i of matrix b is
+ * d_Z[b][i][0..N) (row i = vector i). */
+int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_t batch,
+                          double *d_A, double *d_w, double *d_Z, void *d_work,
+                          int64_t work_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCB200_H */

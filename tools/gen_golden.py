@@ -1,0 +1,356 @@
+"""Freeze golden vectors from the LIVE reference (ARC 3.10.2 CPU path) into tests/golden/.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes
+are committed and are what the GPU box compares against.  The reference is run
+with an EMPTY matrix-element memo so every radial element comes from its live C
+Numerov path (SURVEY.md 8c oracle rules).
+
+    python tools/gen_golden.py [radial] [angular] [stark] [pair] [divalent]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tools.refenv as refenv  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+
+
+def _comp_arrays(comp, width):
+    """list[list[[coef,idx]...]] -> (coef[n,width], idx[n,width]) padded with idx=-1."""
+    n = len(comp)
+    c = np.zeros((n, width))
+    i = -np.ones((n, width), dtype=np.int32)
+    for a, entries in enumerate(comp):
+        for b, (cf, ix) in enumerate(entries[:width]):
+            c[a, b] = float(np.real(cf))
+            i[a, b] = int(ix)
+    return c, i
+
+
+def gen_radial(arc):
+    rng = np.random.default_rng(0)
+    out = {"atoms": {}}
+    for cls, npairs in (("Rubidium", 70), ("Caesium", 12), ("Potassium39", 12)):
+        a = getattr(arc, cls)()
+        dip, quad, wf = [], [], []
+        fixed_d = [(60, 0, .5, 60, 1, 1.5), (60, 0, .5, 70, 1, 1.5), (28, 0, .5, 28, 1, .5),
+                   (20, 0, .5, 120, 1, 1.5), (120, 19, 18.5, 120, 20, 19.5),
+                   (60, 3, 3.5, 61, 4, 4.5), (60, 10, 10.5, 59, 11, 11.5),
+                   (25, 2, 2.5, 26, 3, 3.5)]
+        fixed_q = [(60, 0, .5, 59, 2, 2.5), (60, 1, 1.5, 60, 1, .5), (60, 2, 2.5, 62, 4, 4.5),
+                   (100, 20, 20.5, 100, 20, 19.5), (40, 3, 3.5, 40, 5, 4.5)]
+        pairs_d = list(fixed_d) if cls == "Rubidium" else []
+        pairs_q = list(fixed_q) if cls == "Rubidium" else []
+        while len(pairs_d) < npairs:
+            n1, n2 = int(rng.integers(20, 121)), int(rng.integers(20, 121))
+            l1 = int(rng.integers(0, min(20, n1 - 1) + 1))
+            l2 = l1 + int(rng.choice([-1, 1]))
+            if l2 < 0 or l2 > min(20, n2 - 1):
+                continue
+            j1 = l1 + float(rng.choice([-.5, .5]))
+            j2 = l2 + float(rng.choice([-.5, .5]))
+            if j1 < 0 or j2 < 0 or abs(j1 - j2) > 1.1:
+                continue
+            pairs_d.append((n1, l1, j1, n2, l2, j2))
+        while len(pairs_q) < npairs // 2:
+            n1, n2 = int(rng.integers(20, 121)), int(rng.integers(20, 121))
+            l1 = int(rng.integers(0, min(20, n1 - 1) + 1))
+            l2 = l1 + int(rng.choice([-2, 0, 2]))
+            if l2 < 0 or l2 > min(20, n2 - 1):
+                continue
+            j1 = l1 + float(rng.choice([-.5, .5]))
+            j2 = l2 + float(rng.choice([-.5, .5]))
+            if j1 < 0 or j2 < 0 or abs(j1 - j2) > 2.1 or (n1, l1, j1) == (n2, l2, j2):
+                continue
+            pairs_q.append((n1, l1, j1, n2, l2, j2))
+        t0 = time.time()
+        for p in pairs_d:
+            dip.append(list(p) + [float(a.getRadialMatrixElement(*p))])
+        for p in pairs_q:
+            quad.append(list(p) + [float(a.getQuadrupoleMatrixElement(*p))])
+        # wavefunction-level pins: length, value checksums
+        for (n, l, j) in [(20, 0, .5), (60, 1, 1.5), (60, 10, 10.5), (120, 20, 19.5), (35, 4, 4.5)]:
+            E = a.getEnergy(n, l, j) / 27.211386245981
+            r, psi = a.radialWavefunction(l, 0.5, j, E, a.alphaC ** (1 / 3.0),
+                                          2.0 * n * (n + 15.0), 0.001)
+            nz = int(np.argmax(psi != 0))
+            idx = [nz, nz + 1, len(r) // 3, len(r) // 2, len(r) - 2, len(r) - 1]
+            wf.append({"n": n, "l": l, "j": j, "E_au": E, "L": int(len(r)),
+                       "first_nonzero": nz,
+                       "idx": idx, "r": [float(r[i]) for i in idx],
+                       "psi": [float(psi[i]) for i in idx],
+                       "sum_abs_psi": float(np.abs(psi).sum()),
+                       "sum_psi2_r": float((psi * psi * r).sum())})
+        energies = []
+        for n in (8, 9, 20, 28, 60, 120):
+            for l in range(0, min(n, 8)):
+                for j in (l - .5, l + .5):
+                    if j > 0:
+                        energies.append([n, l, j, float(a.getEnergy(n, l, j))])
+        out["atoms"][cls] = {"dipole": dip, "quadrupole": quad, "wavefunctions": wf,
+                             "energies_eV": energies}
+        print(cls, "radial golden", len(dip), len(quad), "%.1fs" % (time.time() - t0))
+    with open(os.path.join(GOLD, "radial_golden.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
+def gen_angular(arc):
+    from arc.wigner import CG, Wigner3j, Wigner6j, WignerDmatrix
+    from arc.alkali_atom_functions import _EFieldCoupling
+    rng = np.random.default_rng(1)
+    out = {"CG": [], "w3j": [], "w6j": [], "efield": [], "zeeman": [], "wignerD": []}
+    for _ in range(300):
+        j1 = int(rng.integers(0, 12)) / 2
+        j2 = int(rng.integers(0, 6)) / 2
+        j3 = abs(j1 - j2) + int(rng.integers(0, int(2 * min(j1, j2)) + 1))
+        m1 = -j1 + int(rng.integers(0, int(2 * j1) + 1))
+        m2 = -j2 + int(rng.integers(0, int(2 * j2) + 1))
+        m3 = m1 + m2
+        if abs(m3) > j3:
+            continue
+        out["CG"].append([j1, m1, j2, m2, j3, m3, float(CG(j1, m1, j2, m2, j3, m3))])
+        out["w3j"].append([j1, j2, j3, m1, m2, -m3, float(Wigner3j(j1, j2, j3, m1, m2, -m3))])
+    for _ in range(200):
+        l = int(rng.integers(0, 8)); s = .5
+        j = l + float(rng.choice([-.5, .5]))
+        c = int(rng.integers(1, 3))
+        l1 = l + int(rng.integers(-c, c + 1))
+        j1 = l1 + float(rng.choice([-.5, .5]))
+        if j < 0 or j1 < 0 or l1 < 0 or abs(j - j1) > c:
+            continue
+        try:
+            out["w6j"].append([l, s, j, j1, c, l1, float(Wigner6j(l, s, j, j1, c, l1))])
+        except Exception:
+            pass
+    ef = _EFieldCoupling()
+    for s in (0.5, 0, 1):
+        for _ in range(60):
+            l1 = int(rng.integers(0, 10))
+            l2 = l1 + int(rng.choice([-1, 1]))
+            if l2 < 0:
+                continue
+            j1 = l1 + float(rng.choice(np.arange(-s, s + .1, 1)))
+            j2 = l2 + float(rng.choice(np.arange(-s, s + .1, 1)))
+            if j1 < 0 or j2 < 0:
+                continue
+            mj = -min(j1, j2) + int(rng.integers(0, int(2 * min(j1, j2)) + 1))
+            out["efield"].append([l1, j1, mj, l2, j2, mj, s,
+                                  float(ef.getAngular(l1, j1, mj, l2, j2, mj, s=s))])
+    a = arc.Rubidium()
+    for _ in range(40):
+        l = int(rng.integers(0, 6)); j = l + float(rng.choice([-.5, .5]))
+        if j < 0:
+            continue
+        mj = -j + int(rng.integers(0, int(2 * j) + 1))
+        out["zeeman"].append([l, j, mj, 1e-3, 0.5, float(a.getZeemanEnergyShift(l, j, mj, 1e-3))])
+    for theta, phi in ((0.7, 0.0), (np.pi / 4, 0.0), (1.3, 0.4)):
+        wgd = WignerDmatrix(theta, phi)
+        for j in (0.5, 1.5, 2.5, 4.5, 1.0, 2.0):
+            m = wgd.get(j)
+            m = np.asarray(m.todense() if hasattr(m, "todense") else m)
+            out["wignerD"].append({"theta": theta, "phi": phi, "j": j,
+                                   "re": np.real(m).tolist(), "im": np.imag(m).tolist()})
+    with open(os.path.join(GOLD, "angular_golden.json"), "w") as f:
+        json.dump(out, f)
+    print("angular golden", {k: len(v) for k, v in out.items()})
+
+
+def _stark_case(arc, atom, args, fields, name, kwargs=None, pol=None):
+    kwargs = kwargs or {}
+    t0 = time.time()
+    c = arc.StarkMap(atom)
+    c.defineBasis(*args, **kwargs)
+    t1 = time.time()
+    c.diagonalise(fields)
+    t2 = time.time()
+    N = len(c.basisStates)
+    cc, ci = [], []
+    for fi in range(len(fields)):
+        a, b = _comp_arrays(c.composition[fi], 3)
+        cc.append(a); ci.append(b)
+    nzr, nzc = np.nonzero(c.mat2)
+    d = dict(args=np.array(args, dtype=float), s=kwargs.get("s", 0.5), Bz=kwargs.get("Bz", 0.0),
+             basisStates=np.array(c.basisStates, dtype=float),
+             indexOfCoupledState=c.indexOfCoupledState,
+             mat1_diag=np.diag(c.mat1).copy(), mat2_rows=nzr.astype(np.int32),
+             mat2_cols=nzc.astype(np.int32), mat2_vals=c.mat2[nzr, nzc],
+             fields=np.array(fields, dtype=float), y=np.array(c.y),
+             highlight=np.array(c.highlight), comp_c=np.array(cc), comp_i=np.array(ci),
+             t_defineBasis=t1 - t0, t_diagonalise=t2 - t1)
+    if pol is not None:
+        d["polarizability"] = float(c.getPolarizability(**pol))
+    np.savez_compressed(os.path.join(GOLD, name), **d)
+    print(name, "N", N, "defineBasis %.1fs diagonalise %.1fs" % (t1 - t0, t2 - t1),
+          d.get("polarizability"))
+
+
+def gen_stark(arc):
+    a = arc.Rubidium()
+    # C1 (BASELINE.json configs[0]); 13 of the 600 fields kept (indices 0,50,...,550,599)
+    F = np.linspace(0, 600, 600)
+    _stark_case(arc, a, (28, 0, 0.5, 0.5, 23, 32, 20), F[list(range(0, 600, 50)) + [599]],
+                "stark_c1_golden.npz")
+    # reference test/test_single_atom.py:5-14  (853.2 +- 0.1)
+    _stark_case(arc, a, (75, 0, 0.5, 0.5, 70, 80, 20), np.linspace(0.3, 20, 100)[::9],
+                "stark_rb75s_golden.npz")
+    # small cases: Bz != 0, |mj|=1.5
+    _stark_case(arc, a, (30, 2, 2.5, 1.5, 28, 32, 8), np.linspace(0, 2000, 5),
+                "stark_small_bz_golden.npz", kwargs={"Bz": 1e-3})
+
+
+def gen_stark_full_pol(arc):
+    """Full test_single_atom run for the polarizability pin (y of tracked state only)."""
+    a = arc.Rubidium()
+    c = arc.StarkMap(a)
+    c.defineBasis(75, 0, 0.5, 0.5, 70, 80, 20)
+    F = np.linspace(0.3, 20, 100)
+    c.diagonalise(F)
+    p = c.getPolarizability(minStateContribution=0.9)
+    with open(os.path.join(GOLD, "stark_rb75s_pol.json"), "w") as f:
+        json.dump({"polarizability": float(p), "reference_test_value": 853.2, "tol": 0.1}, f)
+    print("Rb75S polarizability", p)
+
+
+def _pair_case(arc, atom, ctor, basis, Rs, k, name, kwargs=None):
+    kwargs = kwargs or {}
+    t0 = time.time()
+    p = arc.PairStateInteractions(atom, *ctor, **kwargs)
+    p.defineBasis(*basis[:5], **({"Bz": basis[5]} if len(basis) > 5 else {}))
+    t1 = time.time()
+    N = len(p.basisStates)
+    p.diagonalise(np.array(Rs, dtype=float), k)
+    t2 = time.time()
+    rng = np.random.default_rng(7)
+    probes = rng.standard_normal((N, 3))
+    d = dict(ctor=np.array(ctor, dtype=float), basis=np.array(basis, dtype=float),
+             interactionsUpTo=kwargs.get("interactionsUpTo", 1),
+             channel=np.array(p.channel, dtype=float),
+             basisStates=np.array(p.basisStates, dtype=float),
+             index=np.array(p.index, dtype=np.int32),
+             originalPairStateIndex=p.originalPairStateIndex,
+             matDiagonal=np.asarray(p.matDiagonal.diagonal()),
+             probes=probes, r=np.array(p.r), y=np.array(p.y),
+             highlight=np.array(p.highlight), k=k,
+             t_defineBasis=t1 - t0, t_diagonalise=t2 - t1)
+    for o, m in enumerate(p.matR):
+        if np.iscomplexobj(m.data):
+            raise RuntimeError("complex matR not supported in golden")
+        d["matR%d_nnz" % o] = m.nnz
+        d["matR%d_sumabs" % o] = float(abs(m).sum())
+        d["matR%d_probe" % o] = m.dot(probes)
+        if N <= 800:
+            coo = m.tocoo()
+            d["matR%d_rows" % o] = coo.row.astype(np.int32)
+            d["matR%d_cols" % o] = coo.col.astype(np.int32)
+            d["matR%d_vals" % o] = coo.data
+    for o, c in enumerate(p.coupling):
+        d["coupling%d_nnz" % o] = c.nnz
+        d["coupling%d_sumabs" % o] = float(abs(c).sum())
+    # dense cross-check of eigsh (SURVEY 8c iv): k nearest sigma=0 from numpy eigh
+    yd = []
+    for rval in p.r:
+        m = p.matDiagonal
+        rX = (rval * 1e-6) ** 3
+        for mr in p.matR:
+            m = m + mr / rX
+            rX *= rval * 1e-6
+        w = np.linalg.eigvalsh(m.toarray())
+        sel = np.sort(np.argsort(np.abs(w), kind="stable")[:min(k, N - 1)])
+        yd.append(w[sel])
+    d["y_dense"] = np.array(yd)
+    np.savez_compressed(os.path.join(GOLD, name), **d)
+    print(name, "N", N, "channels", len(p.channel), "nnz", p.matR[0].nnz,
+          "defineBasis %.1fs diagonalise %.1fs" % (t1 - t0, t2 - t1))
+
+
+def gen_pair(arc, big=True):
+    a = arc.Rubidium()
+    # small cases first (fast): theta=0; theta!=0 with Bz; quadrupole terms
+    _pair_case(arc, a, (60, 0, .5, 60, 0, .5, .5, .5), (0, 0, 2, 3, 8e9),
+               [1.5, 3.0, 8.0], 40, "pair_small_theta0_golden.npz")
+    _pair_case(arc, a, (40, 2, 2.5, 40, 2, 2.5, 2.5, 2.5), (np.pi / 4, 0, 1, 3, 6e9, 1e-4),
+               [2.0, 4.0, 9.0], 60, "pair_small_theta_bz_golden.npz")
+    _pair_case(arc, a, (50, 1, 1.5, 50, 1, 1.5, 1.5, .5), (0.3, 0, 1, 3, 5e9),
+               [1.2, 5.0], 30, "pair_small_quad_golden.npz", kwargs={"interactionsUpTo": 2})
+    if big:
+        # C3 (BASELINE.json configs[2]); 3 of the 1000 R points + 3 more
+        _pair_case(arc, a, (60, 0, .5, 60, 0, .5, .5, .5), (0, 0, 5, 5, 25e9),
+                   [1.0, 2.5, 4.0, 5.5, 7.75, 10.0], 250, "pair_c3_golden.npz")
+
+
+def gen_divalent(arc):
+    a = arc.Strontium88()
+    rng = np.random.default_rng(3)
+    out = {"dipole": [], "quadrupole": [], "energies_eV": []}
+    for s in (0, 1):
+        cnt = 0
+        while cnt < 40:
+            n1, n2 = int(rng.integers(40, 75)), int(rng.integers(40, 75))
+            l1 = int(rng.integers(0, 25))
+            l2 = l1 + int(rng.choice([-1, 1]))
+            if l2 < 0 or l1 >= n1 or l2 >= n2:
+                continue
+            j1 = l1 + int(rng.integers(-s, s + 1)); j2 = l2 + int(rng.integers(-s, s + 1))
+            if j1 < 0 or j2 < 0 or (s == 1 and (l1 == 0 and j1 != 1 or l2 == 0 and j2 != 1)):
+                continue
+            try:
+                v = float(a.getRadialMatrixElement(n1, l1, j1, n2, l2, j2, s=s))
+            except Exception:
+                continue
+            out["dipole"].append([n1, l1, j1, n2, l2, j2, s, v]); cnt += 1
+        cnt = 0
+        while cnt < 20:
+            n1, n2 = int(rng.integers(40, 75)), int(rng.integers(40, 75))
+            l1 = int(rng.integers(0, 25))
+            l2 = l1 + int(rng.choice([-2, 0, 2]))
+            if l2 < 0 or l1 >= n1 or l2 >= n2:
+                continue
+            j1 = l1 + int(rng.integers(-s, s + 1)); j2 = l2 + int(rng.integers(-s, s + 1))
+            if j1 < 0 or j2 < 0 or (s == 1 and (l1 == 0 and j1 != 1 or l2 == 0 and j2 != 1)):
+                continue
+            try:
+                v = float(a.getQuadrupoleMatrixElement(n1, l1, j1, n2, l2, j2, s=s))
+            except Exception:
+                continue
+            out["quadrupole"].append([n1, l1, j1, n2, l2, j2, s, v]); cnt += 1
+        for n in (45, 60, 70):
+            for l in range(0, 8):
+                for j in range(max(l - s, 0), l + s + 1):
+                    if s == 1 and l == 0 and j != 1:
+                        continue
+                    try:
+                        out["energies_eV"].append([n, l, j, s, float(a.getEnergy(n, l, j, s=s))])
+                    except Exception:
+                        pass
+    with open(os.path.join(GOLD, "divalent_golden.json"), "w") as f:
+        json.dump(out, f)
+    print("divalent golden", {k: len(v) for k, v in out.items()})
+    # small Sr88 singlet Stark map
+    _stark_case(arc, a, (55, 0, 0, 0, 53, 57, 12), np.linspace(0, 100, 4),
+                "stark_sr88_singlet_golden.npz", kwargs={"s": 0})
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
+    arc = refenv.load(home_name="home_golden_" + "_".join(what))
+    if "radial" in what:
+        gen_radial(arc)
+    if "angular" in what:
+        gen_angular(arc)
+    if "stark" in what:
+        gen_stark(arc)
+    if "starkpol" in what:
+        gen_stark_full_pol(arc)
+    if "pairsmall" in what:
+        gen_pair(arc, big=False)
+    if "pair" in what:
+        gen_pair(arc, big=True)
+    if "divalent" in what:
+        gen_divalent(arc)
