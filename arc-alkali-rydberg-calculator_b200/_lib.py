@@ -45,6 +45,10 @@ _SIGNATURES = {
     "arcb200_scatter_coo": (c_int, [c_int, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_syevd_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                                       c_i64]),
+    "arcb200_sytrd_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_i64, c_i32]),
+    "arcb200_stedc_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_i64]),
 }
 
 

@@ -1,0 +1,71 @@
+// eig.cuh -- workspace layout and internal interfaces of the batched symmetric
+// eigensolver (subsystem 3).  All matrices are stored column-major with leading
+// dimension Npad = N rounded up to 32; only the lower triangle of A is referenced.
+#pragma once
+#include "common.cuh"
+
+constexpr int EIG_PB = 32;          // panel width = tile width
+constexpr int EIG_MAX_NODES = 512;  // merges per level per matrix (N <= 32768)
+constexpr int EIG_PROB_BYTES = 96;  // >= sizeof(GemmProblem)
+
+struct EigLayout {
+    int N, Npad, NB, nvec;
+    // per-slot element offsets (in doubles) inside the slot
+    size_t oA, oQ1, oQ2, oU, oWp, oVp, oTrans, oWdir, oD, oE, oTau, oScr, oTfac, oLam, oAux;
+    size_t slot_doubles;
+    // int workspace per slot (in int32)
+    size_t oPerm, oIdx, slot_ints;
+};
+
+static inline size_t eig_align(size_t x) { return (x + 31) & ~(size_t)31; }
+
+static inline EigLayout eig_layout(int N, int nvec)
+{
+    EigLayout L;
+    L.N = N;
+    L.Npad = (N + 31) & ~31;
+    L.NB = L.Npad / 32;
+    L.nvec = nvec;
+    const size_t np = (size_t)L.Npad;
+    size_t o = 0;
+    L.oA = o;      o += np * np;
+    L.oQ1 = o;     o += np * np;
+    L.oQ2 = o;     o += np * np;
+    L.oU = o;      o += np * np;
+    L.oWp = o;     o += np * EIG_PB;
+    L.oVp = o;     o += np * EIG_PB;
+    L.oTrans = o;  o += (size_t)L.NB * np;
+    L.oWdir = o;   o += np;
+    L.oD = o;      o += np;
+    L.oE = o;      o += np;
+    L.oTau = o;    o += np;
+    L.oScr = o;    o += 4096;                       // cluster exchange scratch
+    L.oTfac = o;   o += (size_t)L.NB * EIG_PB * EIG_PB;   // T factors of the block reflectors
+    L.oLam = o;    o += np;                         // eigenvalues
+    L.oAux = o;    o += 12 * np;                    // D&C vectors (z, dlamda, w, ...)
+    L.slot_doubles = eig_align(o);
+    size_t oi = 0;
+    L.oPerm = oi;  oi += 8 * np;
+    L.oIdx = oi;   oi += 4 * np;
+    L.slot_ints = eig_align(oi);
+    return L;
+}
+
+struct EigSlots {
+    EigLayout L;
+    double *dbl;       // batch * slot_doubles
+    int32_t *ints;     // batch * slot_ints
+    int batch;
+    void *gemm_probs;  // batch * EIG_MAX_NODES GemmProblem descriptors
+    __host__ __device__ double *slot(int b) const { return dbl + (size_t)b * L.slot_doubles; }
+    __host__ __device__ int32_t *islot(int b) const { return ints + (size_t)b * L.slot_ints; }
+};
+
+// stage 1: A (lower, column-major, lda=Npad) -> d, e, Householder vectors in A, tau
+int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *launches);
+// stage 2: (d, e) -> eigenvalues (ascending, in oLam) and eigenvectors of T in Q1
+int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
+// stage 3: Z = Q_house * Q1[:, sel0 : sel0+nsel]  (in place on Q1 columns)
+int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
+              int *launches);
+int eig_pick_cluster(int N, int nmat);

@@ -1,0 +1,411 @@
+// eig_sweep.cu -- subsystem (2) Hamiltonian assembly, the fused result epilogue and the
+// C-ABI sweep entry points (include/arcb200.h).
+//
+//   assemble  H(F) = diag(h0) + F V           (calculations_atom_single.py:984)
+//             H(R) = diag(h0) + sum_o M_o / (R 1e-6)^(3+o)   (calculations_atom_pairstate.py:3435-3440)
+//             written straight into the eigensolver's batch workspace (lower-triangle
+//             32x32 tiles only, coalesced; V / M_o are read through L2 once per batch)
+//   solve     eig_sytrd -> eig_stedc -> [select k nearest sigma] -> eig_ormtr
+//   epilogue  y, highlight and the top-k composition per eigenvector, so eigenvectors
+//             never leave the GPU (calculations_atom_single.py:988-1021, 1395-1416;
+//             calculations_atom_pairstate.py:3494-3520).
+#include "eig.cuh"
+
+namespace {
+
+struct WorkView {
+    EigSlots S;
+    int32_t *sel0;      // per slot: first selected eigenvector
+};
+
+size_t work_bytes(const EigLayout &L, int batch)
+{
+    size_t b = 256;
+    b += (size_t)batch * L.slot_doubles * sizeof(double);
+    b += (size_t)batch * L.slot_ints * sizeof(int32_t);
+    b += (size_t)batch * EIG_MAX_NODES * EIG_PROB_BYTES;
+    b += (size_t)batch * sizeof(int32_t) + 256;
+    return b;
+}
+
+WorkView carve(void *d_work, const EigLayout &L, int batch)
+{
+    WorkView W;
+    uintptr_t p = ((uintptr_t)d_work + 255) & ~(uintptr_t)255;
+    W.S.L = L;
+    W.S.batch = batch;
+    W.S.dbl = (double *)p;
+    p += (size_t)batch * L.slot_doubles * sizeof(double);
+    W.S.ints = (int32_t *)p;
+    p += (size_t)batch * L.slot_ints * sizeof(int32_t);
+    W.S.gemm_probs = (void *)p;
+    p += (size_t)batch * EIG_MAX_NODES * EIG_PROB_BYTES;
+    W.sel0 = (int32_t *)p;
+    return W;
+}
+
+// ---------------------------------------------------------------- assembly
+// grid = (ntiles_lower, nmat); one 32x32 tile per CTA of 256 threads (8 columns / pass)
+__global__ void __launch_bounds__(256) assemble_stark_kernel(
+    int N, int Npad, double *base, size_t slot, size_t oA, const double *__restrict__ h0,
+    const double *__restrict__ V, const double *__restrict__ F, int f0)
+{
+    // tile index -> (I, J), J <= I
+    const int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int mat = blockIdx.y;
+    double *A = base + (size_t)mat * slot + oA;
+    const double f = F[f0 + mat];
+    const int r = 32 * I + (threadIdx.x & 31);
+    for (int cc = threadIdx.x >> 5; cc < 32; cc += 8) {
+        const int c = 32 * J + cc;
+        double x = 0.0;
+        if (r < N && c < N) {
+            // mat1 + mat2*F, elementwise like numpy (mat2 symmetric: V[c][r] == V[r][c])
+            x = __dmul_rn(V[(size_t)c * N + r], f);
+            if (r == c) x = __dadd_rn(h0[r], x);
+        }
+        A[r + (size_t)c * Npad] = x;
+    }
+}
+
+__global__ void __launch_bounds__(256) assemble_pair_kernel(
+    int N, int Npad, double *base, size_t slot, size_t oA, const double *__restrict__ h0,
+    int norders, const double *const *__restrict__ M, const double *__restrict__ R, int p0)
+{
+    const int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int mat = blockIdx.y;
+    double *A = base + (size_t)mat * slot + oA;
+    const double x1 = __dmul_rn(R[p0 + mat], 1.0e-6);
+    const int r = 32 * I + (threadIdx.x & 31);
+    for (int cc = threadIdx.x >> 5; cc < 32; cc += 8) {
+        const int c = 32 * J + cc;
+        double x = 0.0;
+        if (r < N && c < N) {
+            if (r == c) x = h0[r];
+            double rX = __dmul_rn(__dmul_rn(x1, x1), x1);          // (R*1e-6)**3
+            for (int o = 0; o < norders; ++o) {
+                x = __dadd_rn(x, __ddiv_rn(M[o][(size_t)c * N + r], rX));   // m = m + matRX / rX
+                rX = __dmul_rn(rX, x1);
+            }
+        }
+        A[r + (size_t)c * Npad] = x;
+    }
+}
+
+__global__ void scatter_coo_kernel(int N, int64_t nnz, const int32_t *__restrict__ rows,
+                                   const int32_t *__restrict__ cols,
+                                   const double *__restrict__ vals, double *__restrict__ dense)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        // scipy's csr_matrix((v,(r,c))) sums duplicate entries
+        atomicAdd(&dense[(size_t)rows[i] * N + cols[i]], vals[i]);
+    }
+}
+
+__global__ void load_dense_kernel(int N, int Npad, double *base, size_t slot, size_t oA,
+                                  const double *__restrict__ src)
+{
+    const int mat = blockIdx.y;
+    double *A = base + (size_t)mat * slot + oA;
+    const double *S = src + (size_t)mat * N * N;
+    const size_t total = (size_t)Npad * Npad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % Npad), c = (int)(i / Npad);
+        A[i] = (r < N && c < N) ? S[(size_t)c * N + r] : 0.0;
+    }
+}
+
+__global__ void store_dense_kernel(int N, int Npad, const double *base, size_t slot, size_t oQ,
+                                   size_t oLam, double *__restrict__ Zout, double *__restrict__ wout)
+{
+    const int mat = blockIdx.y;
+    const double *Q = base + (size_t)mat * slot + oQ;
+    const double *lam = base + (size_t)mat * slot + oLam;
+    const size_t total = (size_t)N * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % N), c = (int)(i / N);
+        Zout[(size_t)mat * total + i] = Q[r + (size_t)c * Npad];
+        if (i < (size_t)N) wout[(size_t)mat * N + i] = lam[i];
+    }
+}
+
+// ---------------------------------------------------------------- selection
+// k eigenvalues nearest sigma form a contiguous window of the ascending spectrum.
+__global__ void select_window_kernel(int N, const double *base, size_t slot, size_t oLam, int k,
+                                     double sigma, int32_t *sel0, int nmat)
+{
+    const int mat = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mat >= nmat) return;
+    const double *lam = base + (size_t)mat * slot + oLam;
+    int lo = 0, hi = N;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (lam[m] < sigma) lo = m + 1; else hi = m; }
+    int left = lo - 1, right = lo;    // next candidates
+    for (int t = 0; t < k; ++t) {
+        const bool canL = left >= 0, canR = right < N;
+        if (canL && (!canR || fabs(lam[left] - sigma) <= fabs(lam[right] - sigma))) --left;
+        else ++right;
+    }
+    sel0[mat] = left + 1;
+}
+
+// ---------------------------------------------------------------- epilogue
+// one warp per eigenvector: eigenvalue, highlight, top-k composition
+constexpr int MAXTOP = 8;
+__global__ void __launch_bounds__(256) epilogue_kernel(
+    int N, int Npad, const double *base, size_t slot, size_t oQ, size_t oLam,
+    const int32_t *__restrict__ sel0, int nsel, int idx0, const double *__restrict__ drive_w,
+    int topk, double contrib_max, double *__restrict__ y, double *__restrict__ hl,
+    double *__restrict__ comp_c, int32_t *__restrict__ comp_i, int point0)
+{
+    const int mat = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= nsel) return;
+    const int s0 = sel0 ? sel0[mat] : 0;
+    const double *q = base + (size_t)mat * slot + oQ + (size_t)(s0 + i) * Npad;
+    const double *lam = base + (size_t)mat * slot + oLam;
+    const size_t orow = (size_t)(point0 + mat) * nsel + i;
+    double best_a[MAXTOP];
+    int best_i[MAXTOP];
+#pragma unroll
+    for (int t = 0; t < MAXTOP; ++t) { best_a[t] = -1.0; best_i[t] = -1; }
+    double hacc = 0.0;
+    for (int r = lane; r < N; r += 32) {
+        const double c = q[r];
+        const double a = fabs(c);
+        if (drive_w) hacc += drive_w[r] * (c * c);
+        if (a > best_a[MAXTOP - 1] && topk > 0) {
+            // insertion into the lane-local sorted list
+            double ca = a; int ci = r;
+#pragma unroll
+            for (int t = 0; t < MAXTOP; ++t) {
+                if (ca > best_a[t]) {
+                    const double ta = best_a[t]; const int ti = best_i[t];
+                    best_a[t] = ca; best_i[t] = ci; ca = ta; ci = ti;
+                }
+            }
+        }
+    }
+    if (drive_w) hacc = warp_sum(hacc);
+    if (lane == 0) {
+        y[orow] = lam[s0 + i];
+        hl[orow] = drive_w ? hacc : q[idx0] * q[idx0];
+    }
+    // warp merge: pop the global maximum topk times
+    double total = 0.0;
+    const int kk = min(topk, MAXTOP);
+    for (int t = 0; t < kk; ++t) {
+        const bool go = total < contrib_max;
+        double a = best_a[0];
+        int src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oa = __shfl_xor_sync(ARCB200_FULL_MASK, a, o);
+            const int os = __shfl_xor_sync(ARCB200_FULL_MASK, src, o);
+            if (oa > a || (oa == a && os < src)) { a = oa; src = os; }
+        }
+        const int widx = __shfl_sync(ARCB200_FULL_MASK, best_i[0], src);
+        if (lane == src) {
+#pragma unroll
+            for (int u = 0; u < MAXTOP - 1; ++u) { best_a[u] = best_a[u + 1]; best_i[u] = best_i[u + 1]; }
+            best_a[MAXTOP - 1] = -1.0; best_i[MAXTOP - 1] = -1;
+        }
+        if (lane == 0) {
+            const bool valid = go && widx >= 0;
+            comp_c[orow * topk + t] = valid ? q[widx] : 0.0;
+            comp_i[orow * topk + t] = valid ? widx : -1;
+        }
+        if (go && widx >= 0) total += a * a;
+    }
+    if (lane == 0)
+        for (int t = kk; t < topk; ++t) { comp_c[orow * topk + t] = 0.0; comp_i[orow * topk + t] = -1; }
+}
+
+int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma,
+                cudaStream_t st, int *launches)
+{
+    const EigLayout &L = W.S.L;
+    const int cluster = eig_pick_cluster(L.N, nmat);
+    int rc = eig_sytrd(W.S, nmat, cluster, st, launches);
+    if (rc) return rc;
+    rc = eig_stedc(W.S, nmat, st, launches);
+    if (rc) return rc;
+    const int32_t *sel = nullptr;
+    if (window) {
+        select_window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(
+            L.N, W.S.dbl, L.slot_doubles, L.oLam, nsel, sigma, W.sel0, nmat);
+        *launches += 1;
+        sel = W.sel0;
+    }
+    return eig_ormtr(W.S, nmat, sel, nsel, st, launches);
+}
+
+}  // namespace
+
+extern "C" int64_t arcb200_sweep_workspace_bytes(int32_t N, int32_t batch, int32_t nvec)
+{
+    if (N < 1 || batch < 1) return -1;
+    return (int64_t)work_bytes(eig_layout(N, nvec), batch);
+}
+
+extern "C" int arcb200_scatter_coo(int device, void *stream, int32_t N, int64_t nnz,
+                                   const int32_t *d_rows, const int32_t *d_cols,
+                                   const double *d_vals, double *d_dense)
+{
+    if (nnz <= 0) return 0;
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    scatter_coo_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(N, nnz, d_rows, d_cols, d_vals, d_dense);
+    ARCB200_LAUNCH_CHECK("scatter_coo_kernel");
+    return 0;
+}
+
+extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
+                                   const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
+                                   const double *d_drive_w, int32_t topk, double contrib_max,
+                                   double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
+                                   void *d_work, int64_t wbytes, int32_t batch)
+{
+    if (nF <= 0) return 0;
+    if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, N);
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    const int ntiles = L.NB * (L.NB + 1) / 2;
+    int launches = 0;
+    for (int f0 = 0; f0 < nF; f0 += batch) {
+        const int nmat = min(batch, nF - f0);
+        assemble_stark_kernel<<<dim3(ntiles, nmat), 256, 0, st>>>(
+            N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_h0diag, d_V, d_F, f0);
+        ++launches;
+        int rc = solve_batch(W, nmat, N, false, 0.0, st, &launches);
+        if (rc) return rc;
+        const int tk = topk > 0 ? topk : 1;
+        epilogue_kernel<<<dim3((N + 7) / 8, nmat), 256, 0, st>>>(
+            N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, nullptr, N, idx0, d_drive_w,
+            topk > 0 ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, f0);
+        (void)tk;
+        ++launches;
+    }
+    ARCB200_LAUNCH_CHECK("stark sweep");
+    return launches;
+}
+
+extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
+                                  int32_t norders, const double *const *d_M, int32_t nR,
+                                  const double *d_R, int32_t k, double sigma, int32_t opi,
+                                  const double *d_drive_w, int32_t topk, double *d_y, double *d_hl,
+                                  double *d_comp_c, int32_t *d_comp_i, void *d_work,
+                                  int64_t wbytes, int32_t batch)
+{
+    if (nR <= 0) return 0;
+    if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
+    if (k < 1 || k > N) { arcb200_set_error("k must be in [1, N]"); return -1; }
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, k);
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    const int ntiles = L.NB * (L.NB + 1) / 2;
+    int launches = 0;
+    for (int p0 = 0; p0 < nR; p0 += batch) {
+        const int nmat = min(batch, nR - p0);
+        assemble_pair_kernel<<<dim3(ntiles, nmat), 256, 0, st>>>(
+            N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_h0diag, norders, d_M, d_R, p0);
+        ++launches;
+        int rc = solve_batch(W, nmat, k, true, sigma, st, &launches);
+        if (rc) return rc;
+        epilogue_kernel<<<dim3((k + 7) / 8, nmat), 256, 0, st>>>(
+            N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w, topk,
+            2.0, d_y, d_hl, d_comp_c, d_comp_i, p0);
+        ++launches;
+    }
+    ARCB200_LAUNCH_CHECK("pair sweep");
+    return launches;
+}
+
+extern "C" int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_t batch,
+                                     double *d_A, double *d_w, double *d_Z, void *d_work,
+                                     int64_t wbytes)
+{
+    if (batch <= 0) return 0;
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, N);
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    int launches = 0;
+    load_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_A);
+    int rc = solve_batch(W, batch, N, false, 0.0, st, &launches);
+    if (rc) return rc;
+    store_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1,
+                                                         L.oLam, d_Z, d_w);
+    ARCB200_LAUNCH_CHECK("syevd");
+    return launches + 2;
+}
+
+// ---------------------------------------------------------------- stage-level entry points
+__global__ void copy_vec_kernel(int N, const double *base, size_t slot, size_t off, double *out)
+{
+    const int mat = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        out[(size_t)mat * N + i] = base[(size_t)mat * slot + off + i];
+}
+__global__ void put_vec_kernel(int N, double *base, size_t slot, size_t off, const double *in)
+{
+    const int mat = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        base[(size_t)mat * slot + off + i] = in[(size_t)mat * N + i];
+}
+
+extern "C" int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
+                                     const double *d_A, double *d_d, double *d_e, double *d_tau,
+                                     void *d_work, int64_t wbytes, int32_t cluster)
+{
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, N);
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    int launches = 0;
+    load_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_A);
+    int rc = eig_sytrd(W.S, batch, cluster > 0 ? cluster : eig_pick_cluster(N, batch), st, &launches);
+    if (rc) return rc;
+    copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oD, d_d);
+    copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oE, d_e);
+    if (d_tau) copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oTau, d_tau);
+    ARCB200_LAUNCH_CHECK("sytrd_batched");
+    return launches + 3;
+}
+
+extern "C" int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
+                                     const double *d_d, const double *d_e, double *d_w,
+                                     double *d_Q, void *d_work, int64_t wbytes)
+{
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, N);
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    int launches = 0;
+    put_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oD, d_d);
+    put_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oE, d_e);
+    int rc = eig_stedc(W.S, batch, st, &launches);
+    if (rc) return rc;
+    store_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1,
+                                                         L.oLam, d_Q, d_w);
+    ARCB200_LAUNCH_CHECK("stedc_batched");
+    return launches + 3;
+}

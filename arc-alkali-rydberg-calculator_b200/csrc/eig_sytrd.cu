@@ -1,0 +1,378 @@
+// eig_sytrd.cu -- stage 1 of the batched symmetric eigensolver: blocked Householder
+// tridiagonalisation, one thread-block CLUSTER per matrix (sm_100a).
+//
+// Algorithm: LAPACK dsytrd/dlatrd, UPLO='L', panel width 32, written for a cluster of
+// C CTAs x 8 warps.  Block-row I (32 rows) of the lower triangle is owned by cluster-warp
+// (I mod 8C); the owner is the only writer of those rows of A, Vp, Wp.
+//   per column c of a panel (3 cluster barriers):
+//     phase 1  lazy update of column c with the panel's (V, W); norm partials
+//     phase 2  v = Householder vector; symmetric mat-vec  w = A v  on the lower
+//              triangle: each 32x32 tile is read ONCE (coalesced, lane <-> row) and used
+//              for both A_IJ v_J (registers) and A_IJ^T v_I (via a padded shared-memory
+//              transpose, lane <-> column) -- algorithmic HBM bytes 4 N^3 / 3 per matrix;
+//              panel dot products W^T v, V^T v ride along
+//     phase 3  w -= V (W^T v) + W (V^T v); w *= tau; partial w.v
+//     phase 4  w -= (tau/2)(w.v) v  -> column of W
+//   per panel: trailing update A -= V W^T + W V^T with FP64 tensor-core DMMA tiles
+//   (mma.sync.m8n8k4.f64), fragments read straight from the 32-wide panels.
+// Vectors are exchanged through L2 (ld.global.cg) between cluster barriers.
+#include <cooperative_groups.h>
+#include "eig.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int SY_WARPS = 8;
+constexpr int SY_THREADS = SY_WARPS * 32;
+constexpr int TPAD = 33;
+
+struct SytrdArgs {
+    int N, Npad, NB;
+    double *base;            // slot 0
+    size_t slot;             // doubles per slot
+    size_t oA, oWp, oVp, oTrans, oWdir, oD, oE, oTau, oScr;
+};
+
+__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool CL>
+__device__ __forceinline__ void group_sync(cg::cluster_group &cl)
+{
+    if (CL) cl.sync(); else __syncthreads();
+}
+
+template <bool CL>
+__global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = CL ? (int)cluster.num_blocks() : 1;
+    const int rank = CL ? (int)cluster.block_rank() : 0;
+    const int mat = blockIdx.x / C;
+    const int N = a.N, lda = a.Npad, NB = a.NB;
+    double *slot = a.base + (size_t)mat * a.slot;
+    double *__restrict__ A = slot + a.oA;
+    double *__restrict__ Wp = slot + a.oWp;       // [Npad][32] row-major
+    double *__restrict__ Vp = slot + a.oVp;
+    double *__restrict__ trans = slot + a.oTrans; // [NB][Npad]
+    double *__restrict__ wdir = slot + a.oWdir;
+    double *__restrict__ dd = slot + a.oD;
+    double *__restrict__ ee = slot + a.oE;
+    double *__restrict__ tt = slot + a.oTau;
+    double *__restrict__ scr = slot + a.oScr;     // [0]=alpha, [8..8+C)=norm, [32..32+C)=p, [64 + 64*rank ..)=t
+
+    extern __shared__ double smem[];
+    double *v = smem;                              // [Npad]
+    double *tile = smem + lda;                     // [SY_WARPS][32*TPAD]
+    __shared__ double sred[SY_WARPS][64];
+    __shared__ double pv[32], pw[32], t1s[32], t2s[32];
+    __shared__ double sbc[4];
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int gw = rank * SY_WARPS + wid;
+    const int nW = C * SY_WARPS;
+    double *mytile = tile + wid * (32 * TPAD);
+    const int grp = lane >> 2, tig = lane & 3;
+
+    auto first_owned = [&](int I0) { return I0 + ((gw - I0 % nW) + nW) % nW; };
+
+    double pw_last = 0.0;    // W(c, i-1) computed redundantly by every CTA
+
+    for (int k0 = 0; k0 < N; k0 += 32) {
+        const int k1 = min(k0 + 32, N);
+        // zero the panels for the rows this warp owns
+        for (int I = first_owned(k0 / 32); I < NB; I += nW) {
+            for (int q = 0; q < 32; ++q) {
+                Wp[(size_t)(32 * I + q) * 32 + lane] = 0.0;
+                Vp[(size_t)(32 * I + q) * 32 + lane] = 0.0;
+            }
+        }
+        __syncwarp();
+
+        for (int c = k0; c < k1; ++c) {
+            const int i = c - k0;
+            // pivot-row entries V(c, j), W(c, j), j < i
+            if (wid == 0 && lane < i) {
+                pv[lane] = (lane == i - 1) ? 1.0 : __ldcg(&Vp[(size_t)c * 32 + lane]);
+                pw[lane] = (lane == i - 1) ? pw_last : __ldcg(&Wp[(size_t)c * 32 + lane]);
+            }
+            __syncthreads();
+
+            // ---------------- phase 1: lazy update of column c --------------------
+            double nrm = 0.0;
+            for (int I = first_owned(c / 32); I < NB; I += nW) {
+                const int r = 32 * I + lane;
+                if (r >= c && r < N) {
+                    double av = __ldcg(&A[r + (size_t)c * lda]);
+                    const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
+                    for (int j = 0; j < i; ++j) av -= vr[j] * pw[j] + wr[j] * pv[j];
+                    A[r + (size_t)c * lda] = av;
+                    if (r >= c + 2) nrm += av * av;
+                    if (r == c) dd[c] = av;
+                    if (r == c + 1) scr[0] = av;
+                }
+            }
+            if (c == N - 1) break;
+            nrm = warp_sum(nrm);
+            if (lane == 0) sred[wid][0] = nrm;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int q = 0; q < SY_WARPS; ++q) s += sred[q][0];
+                scr[8 + rank] = s;
+            }
+            group_sync<CL>(cluster);                                   // ---- B1
+
+            double alpha = __ldcg(&scr[0]);
+            double xn2 = 0.0;
+            for (int q = 0; q < C; ++q) xn2 += __ldcg(&scr[8 + q]);
+            double tau, beta, scale;
+            if (xn2 == 0.0) {
+                tau = 0.0; beta = alpha; scale = 0.0;
+            } else {
+                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            if (gw == 0 && lane == 0) { ee[c] = beta; tt[c] = tau; }
+            if (tau == 0.0) {
+                // H = I: V column = unit vector (never multiplied by anything but W=0)
+                for (int I = first_owned((c + 1) / 32); I < NB; I += nW) {
+                    const int r = 32 * I + lane;
+                    if (r == c + 1) Vp[(size_t)r * 32 + i] = 1.0;
+                }
+                pw_last = 0.0;
+                __syncthreads();
+                continue;
+            }
+
+            // ---------------- phase 2: v, symmetric mat-vec, panel dots ------------
+            for (int r = tid; r < lda; r += SY_THREADS) {
+                double x = 0.0;
+                if (r == c + 1) x = 1.0;
+                else if (r > c + 1 && r < N) x = __ldcg(&A[r + (size_t)c * lda]) * scale;
+                v[r] = x;
+            }
+            __syncthreads();
+
+            const int Jmin = (c + 1) / 32;
+            double t1acc = 0.0, t2acc = 0.0;
+            for (int I = first_owned(Jmin); I < NB; I += nW) {
+                const int r = 32 * I + lane;
+                double vI[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) vI[q] = v[32 * I + q];
+                if (r >= c + 1) Vp[(size_t)r * 32 + i] = v[r];
+                if (lane < i) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const size_t rr = (size_t)(32 * I + q) * 32 + lane;
+                        t1acc += Wp[rr] * vI[q];
+                        t2acc += Vp[rr] * vI[q];
+                    }
+                }
+                double wr = 0.0;
+                for (int J = Jmin; J <= I; ++J) {
+                    double areg[32];
+                    const double *ap = &A[r + (size_t)(32 * J) * lda];
+#pragma unroll
+                    for (int cc = 0; cc < 32; ++cc) areg[cc] = __ldcg(ap + (size_t)cc * lda);
+                    const double *vJ = &v[32 * J];
+                    if (J < I) {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) wr += areg[cc] * vJ[cc];
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc)
+                            if (cc <= lane) wr += areg[cc] * vJ[cc];
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 32; ++cc) mytile[cc * TPAD + lane] = areg[cc];
+                    __syncwarp();
+                    double s = 0.0;
+                    if (J < I) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) s += mytile[lane * TPAD + q] * vI[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (q > lane) s += mytile[lane * TPAD + q] * vI[q];
+                    }
+                    __syncwarp();
+                    __stcg(&trans[(size_t)I * lda + 32 * J + lane], s);
+                }
+                wdir[r] = wr;
+            }
+            sred[wid][lane] = t1acc;
+            sred[wid][32 + lane] = t2acc;
+            __syncthreads();
+            if (wid == 0) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < SY_WARPS; ++q) { s1 += sred[q][lane]; s2 += sred[q][32 + lane]; }
+                __stcg(&scr[64 + 64 * rank + lane], s1);
+                __stcg(&scr[64 + 64 * rank + 32 + lane], s2);
+            }
+            group_sync<CL>(cluster);                                   // ---- B2
+
+            // ---------------- phase 3 --------------------------------------------
+            if (wid == 0) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < C; ++q) {
+                    s1 += __ldcg(&scr[64 + 64 * q + lane]);
+                    s2 += __ldcg(&scr[64 + 64 * q + 32 + lane]);
+                }
+                t1s[lane] = s1;
+                t2s[lane] = s2;
+            }
+            __syncthreads();
+            double pacc = 0.0;
+            for (int I = first_owned(Jmin); I < NB; I += nW) {
+                const int r = 32 * I + lane;
+                if (r >= c + 1 && r < N) {
+                    double w = wdir[r];
+                    for (int II = I; II < NB; ++II) w += __ldcg(&trans[(size_t)II * lda + r]);
+                    const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
+                    for (int j = 0; j < i; ++j) w -= vr[j] * t1s[j] + wr[j] * t2s[j];
+                    w *= tau;
+                    pacc += w * v[r];
+                    Wp[(size_t)r * 32 + i] = w;
+                }
+            }
+            // every CTA recomputes W(c+1, i) (the next pivot-row entry) redundantly
+            double wpiv = 0.0;
+            if (wid == 0) {
+                const int r = c + 1, I = r / 32;
+                double part = 0.0;
+                for (int II = I + lane; II < NB; II += 32) part += __ldcg(&trans[(size_t)II * lda + r]);
+                if (lane < i)
+                    part -= __ldcg(&Vp[(size_t)r * 32 + lane]) * t1s[lane]
+                            + __ldcg(&Wp[(size_t)r * 32 + lane]) * t2s[lane];
+                part = warp_sum(part);
+                wpiv = (part + __ldcg(&wdir[r])) * tau;
+            }
+            pacc = warp_sum(pacc);
+            if (lane == 0) sred[wid][0] = pacc;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int q = 0; q < SY_WARPS; ++q) s += sred[q][0];
+                __stcg(&scr[32 + rank], s);
+            }
+            group_sync<CL>(cluster);                                   // ---- B3
+
+            // ---------------- phase 4 --------------------------------------------
+            double p = 0.0;
+            for (int q = 0; q < C; ++q) p += __ldcg(&scr[32 + q]);
+            const double alpha2 = -0.5 * tau * p;
+            for (int I = first_owned(Jmin); I < NB; I += nW) {
+                const int r = 32 * I + lane;
+                if (r >= c + 1 && r < N) {
+                    Wp[(size_t)r * 32 + i] += alpha2 * v[r];
+                    if (r >= c + 2) A[r + (size_t)c * lda] = v[r];
+                }
+            }
+            if (wid == 0) {
+                if (lane == 0) sbc[0] = wpiv + alpha2;   // v[c+1] == 1
+            }
+            __syncthreads();
+            pw_last = sbc[0];
+        }  // columns of the panel
+
+        if (k0 + 32 >= N) break;
+        group_sync<CL>(cluster);          // panels complete and visible cluster-wide
+
+        // ---------------- trailing update: A -= V W^T + W V^T  (DMMA) --------------
+        const int Jt = k0 / 32 + 1;
+        for (int I = first_owned(Jt); I < NB; I += nW) {
+            for (int mt = 0; mt < 4; ++mt) {
+                const int ar = 32 * I + 8 * mt + grp;
+                double fv[8], fw[8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    fv[ks] = -Vp[(size_t)ar * 32 + 4 * ks + tig];
+                    fw[ks] = -Wp[(size_t)ar * 32 + 4 * ks + tig];
+                }
+                for (int J = Jt; J <= I; ++J) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int bc = 32 * J + 8 * nt + grp;   // column index held as B row
+                        const int cc = 32 * J + 8 * nt + 2 * tig;
+                        double *cp = &A[ar + (size_t)cc * lda];
+                        double c0 = __ldcg(cp), c1 = __ldcg(cp + lda);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const double bw = __ldcg(&Wp[(size_t)bc * 32 + 4 * ks + tig]);
+                            const double bv = __ldcg(&Vp[(size_t)bc * 32 + 4 * ks + tig]);
+                            dmma8x8x4(c0, c1, fv[ks], bw);
+                            dmma8x8x4(c0, c1, fw[ks], bv);
+                        }
+                        cp[0] = c0;
+                        cp[lda] = c1;
+                    }
+                }
+            }
+        }
+        // other CTAs read this CTA's panel rows as B fragments: nobody may start zeroing
+        // the panels for the next block column before every CTA is done with them
+        group_sync<CL>(cluster);
+    }  // panels
+}
+
+}  // namespace
+
+int eig_pick_cluster(int N, int nmat)
+{
+    // enough matrices to fill 148 SMs with one CTA each -> no cluster; otherwise spread
+    // each matrix over a cluster so the whole GPU streams.
+    int c = 1;
+    while (c < 8 && nmat * c * 2 <= 148 && N >= 64 * c) c *= 2;
+    if (N >= 4096 && c < 8) c = 8;
+    return c;
+}
+
+int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *launches)
+{
+    const EigLayout &L = S.L;
+    SytrdArgs a;
+    a.N = L.N; a.Npad = L.Npad; a.NB = L.NB;
+    a.base = S.dbl; a.slot = L.slot_doubles;
+    a.oA = L.oA; a.oWp = L.oWp; a.oVp = L.oVp; a.oTrans = L.oTrans; a.oWdir = L.oWdir;
+    a.oD = L.oD; a.oE = L.oE; a.oTau = L.oTau; a.oScr = L.oScr;
+    const size_t smem = ((size_t)L.Npad + (size_t)SY_WARPS * 32 * TPAD) * sizeof(double);
+    if (smem > 220 * 1024) {
+        arcb200_set_error("sytrd: N=%d needs %zu bytes of shared memory (max 220 KiB)", L.N, smem);
+        return -1;
+    }
+    if (cluster <= 1) {
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sytrd_kernel<false><<<nmat, SY_THREADS, smem, st>>>(a);
+    } else {
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cluster > 8)
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true>,
+                                                    cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nmat * cluster);
+        cfg.blockDim = dim3(SY_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        ARCB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sytrd_kernel<true>, a));
+    }
+    ARCB200_LAUNCH_CHECK("sytrd_kernel");
+    if (launches) *launches += 1;
+    return 0;
+}

@@ -213,3 +213,46 @@ def syevd_batched(A, device=None):
                                    _lib.ptr(d_w), _lib.ptr(d_Z), _lib.ptr(work), wbytes)
     _lib.check(rc, "arcb200_syevd_batched")
     return d_w.cpu().numpy(), np.ascontiguousarray(d_Z.cpu().numpy().transpose(0, 2, 1))
+
+
+def sytrd_batched(A, cluster=0, device=None):
+    """Stage 1 only: (d, e, tau) of the Householder tridiagonalisation of each A[b]."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[None]
+    batch, N, _ = A.shape
+    d_A = torch.as_tensor(A).to(dev)
+    outs = [torch.zeros((batch, N), dtype=torch.float64, device=dev) for _ in range(3)]
+    wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rc = lib.arcb200_sytrd_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
+                                   _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
+                                   _lib.ptr(work), wbytes, int(cluster))
+    _lib.check(rc, "arcb200_sytrd_batched")
+    return [o.cpu().numpy() for o in outs]
+
+
+def stedc_batched(d, e, device=None):
+    """Stage 2 only: eigen-decomposition of symmetric tridiagonal matrices (d, e)."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    d = np.ascontiguousarray(np.atleast_2d(d), dtype=np.float64)
+    batch, N = d.shape
+    ee = np.zeros((batch, N))
+    ee[:, :N - 1] = np.atleast_2d(e)[:, :N - 1]
+    d_d, d_e = torch.as_tensor(d).to(dev), torch.as_tensor(ee).to(dev)
+    d_w = torch.empty((batch, N), dtype=torch.float64, device=dev)
+    d_Q = torch.empty((batch, N, N), dtype=torch.float64, device=dev)
+    wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rc = lib.arcb200_stedc_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_d),
+                                   _lib.ptr(d_e), _lib.ptr(d_w), _lib.ptr(d_Q), _lib.ptr(work),
+                                   wbytes)
+    _lib.check(rc, "arcb200_stedc_batched")
+    return d_w.cpu().numpy(), np.ascontiguousarray(d_Q.cpu().numpy().transpose(0, 2, 1))

@@ -143,6 +143,18 @@ int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_t batch,
                           double *d_A, double *d_w, double *d_Z, void *d_work,
                           int64_t work_bytes);
 
+/* Stage-level entry points of the eigensolver (LAPACK dsytrd / dstedc equivalents),
+ * exposed for the stage parity tests.  d_A: batch x N x N symmetric; outputs d, e, tau
+ * (batch x N each; e[N-1], tau[N-1] unused).  cluster = CTAs per matrix (0 = auto). */
+int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
+                          const double *d_A, double *d_d, double *d_e, double *d_tau,
+                          void *d_work, int64_t work_bytes, int32_t cluster);
+/* (d, e) -> eigenvalues d_w (ascending) and eigenvectors of the tridiagonal matrix,
+ * d_Q[b][i][0..N) = eigenvector i. */
+int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
+                          const double *d_d, const double *d_e, double *d_w, double *d_Q,
+                          void *d_work, int64_t work_bytes);
+
 #ifdef __cplusplus
 }
 #endif
