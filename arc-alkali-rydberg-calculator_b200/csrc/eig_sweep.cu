@@ -306,9 +306,9 @@ extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const do
 extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
                                   int32_t norders, const double *const *d_M, int32_t nR,
                                   const double *d_R, int32_t k, double sigma, int32_t opi,
-                                  const double *d_drive_w, int32_t topk, double *d_y, double *d_hl,
-                                  double *d_comp_c, int32_t *d_comp_i, void *d_work,
-                                  int64_t wbytes, int32_t batch)
+                                  const double *d_drive_w, int32_t topk, double contrib_max,
+                                  double *d_y, double *d_hl, double *d_comp_c,
+                                  int32_t *d_comp_i, void *d_work, int64_t wbytes, int32_t batch)
 {
     if (nR <= 0) return 0;
     if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
@@ -329,7 +329,7 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
         if (rc) return rc;
         epilogue_kernel<<<dim3((k + 7) / 8, nmat), 256, 0, st>>>(
             N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w, topk,
-            2.0, d_y, d_hl, d_comp_c, d_comp_i, p0);
+            contrib_max, d_y, d_hl, d_comp_c, d_comp_i, p0);
         ++launches;
     }
     ARCB200_LAUNCH_CHECK("pair sweep");

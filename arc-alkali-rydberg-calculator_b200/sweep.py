@@ -143,7 +143,7 @@ class PairOperators:
                                     dtype=torch.int64, device=dev)
 
 
-def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, batch=None,
+def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max=0.95, batch=None,
                distributed=True, to_host=True):
     """k eigenpairs nearest sigma of H(R) for every R (already sorted by the caller,
     calculations_atom_pairstate.py:3307, 3425-3520)."""
@@ -174,7 +174,8 @@ def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, batch=None,
         rc = lib.arcb200_pair_sweep(device, _lib.stream_ptr(device), N, _lib.ptr(ops.d_h0),
                                     len(ops.d_M), _lib.ptr(ops.d_Mptrs), nR, _lib.ptr(d_R),
                                     int(k), float(sigma_ghz), int(opi), _lib.ptr(d_w),
-                                    int(topk), _lib.ptr(y), _lib.ptr(hl), _lib.ptr(comp_c),
+                                    int(topk), float(contrib_max), _lib.ptr(y), _lib.ptr(hl),
+                                    _lib.ptr(comp_c),
                                     _lib.ptr(comp_i), _lib.ptr(work), wbytes, b)
         _lib.check(rc, "arcb200_pair_sweep")
         res.kernel_launches = rc

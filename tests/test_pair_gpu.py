@@ -1,0 +1,79 @@
+"""GPU parity tests for PairStateInteractions.defineBasis/diagonalise against golden
+vectors frozen from the live reference (scipy eigsh results AND the dense numpy.eigh
+k-nearest-sigma selection).  Energies 1e-9 relative to the spectral scale, highlight 1e-6
+(summed over near-degenerate clusters: the reference adds 1e-8 GHz artificial offsets,
+calculations_atom_pairstate.py:3113,3157, so eigenvectors inside a cluster are arbitrary)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(g):
+    import arc_b200
+    atom = arc_b200.Rubidium()
+    c, b = g["ctor"], g["basis"]
+    calc = arc_b200.PairStateInteractions(atom, int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]),
+                                          interactionsUpTo=int(g["interactionsUpTo"]))
+    kw = {"Bz": float(b[5])} if len(b) > 5 else {}
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]), **kw)
+    return calc
+
+
+def _cluster_sums(y, h, tol):
+    cid = np.concatenate([[0], np.cumsum(np.diff(y) > tol)])
+    return np.bincount(cid, weights=h)
+
+
+def _check(calc, g):
+    k = int(g["k"])
+    calc.diagonalise(g["r"], k)
+    assert np.array_equal(np.asarray(calc.r), g["r"])          # descending, like the reference
+    y = np.array(calc.y)
+    scale = max(np.abs(g["y_dense"]).max(), 1e-3)
+    kk = y.shape[1]
+    assert np.abs(y - g["y_dense"][:, :kk]).max() <= 1e-9 * scale
+    assert np.abs(y - g["y"][:, :kk]).max() <= 1e-7 * scale      # eigsh itself: tol=1e-6
+    hl = np.array(calc.highlight)
+    for i in range(len(g["r"])):
+        # interior clusters only (the window edge may cut a cluster differently)
+        a = _cluster_sums(g["y_dense"][i, :kk], hl[i], 1e-6 * scale)
+        b = _cluster_sums(g["y_dense"][i, :kk], g["highlight"][i, :kk], 1e-6 * scale)
+        assert np.abs(a[1:-1] - b[1:-1]).max() <= 1e-6, i
+    # tracked state: energy and admixture of the original pair state
+    j = np.argmax(g["highlight"], axis=1)
+    rows = np.arange(len(j))
+    jm = np.argmax(hl, axis=1)
+    assert np.abs(y[rows, jm] - g["y"][rows, j]).max() <= 1e-7 * scale
+    return calc
+
+
+@pytest.mark.parametrize("name", ["pair_small_theta0_golden.npz", "pair_small_theta_bz_golden.npz",
+                                  "pair_small_quad_golden.npz"])
+def test_pair_small(gold_dir, name):
+    g = np.load(os.path.join(gold_dir, name))
+    calc = _build(g)
+    for o, m in enumerate(calc.matR):
+        assert m.nnz == int(g["matR%d_nnz" % o])
+        ref = g["matR%d_probe" % o]
+        assert np.abs(m.dot(g["probes"]) - ref).max() <= 1e-8 * np.abs(ref).max()
+    calc = _check(calc, g)
+    s = calc.composition[0][0]
+    assert s.startswith("$") and s.endswith("$") and "rangle" in s
+
+
+def test_pair_c3(gold_dir):
+    """BASELINE.json configs[2]: Rb 60S+60S, N=2363, 627 channels, k=250."""
+    g = np.load(os.path.join(gold_dir, "pair_c3_golden.npz"))
+    calc = _build(g)
+    assert len(calc.basisStates) == 2363 and len(calc.channel) == 627
+    assert calc.originalPairStateIndex == 2001
+    assert calc.matR[0].nnz == 238798
+    ref = g["matR0_probe"]
+    assert np.abs(calc.matR[0].dot(g["probes"]) - ref).max() <= 1e-8 * np.abs(ref).max()
+    d = calc.matDiagonal.diagonal()
+    assert np.abs(d - g["matDiagonal"]).max() <= 1e-9 * np.abs(d).max()
+    _check(calc, g)

@@ -1,0 +1,55 @@
+"""CPU tests of the PairStateInteractions host logic (channel enumeration, coupling
+predicate, angular algebra, matDiagonal / matR assembly) against golden vectors from the
+live reference.  Radial elements come from the oracle here (no GPU needed)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_radial import patch_atom_with_oracle
+
+
+def _build(g):
+    import arc_b200
+    atom = patch_atom_with_oracle(arc_b200.Rubidium())
+    c, b = g["ctor"], g["basis"]
+    calc = arc_b200.PairStateInteractions(atom, int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]),
+                                          interactionsUpTo=int(g["interactionsUpTo"]))
+    kw = {"Bz": float(b[5])} if len(b) > 5 else {}
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]), **kw)
+    return calc
+
+
+@pytest.mark.parametrize("name", ["pair_small_theta0_golden.npz", "pair_small_theta_bz_golden.npz",
+                                  "pair_small_quad_golden.npz"])
+def test_define_basis_matches_reference(gold_dir, name):
+    g = np.load(os.path.join(gold_dir, name))
+    calc = _build(g)
+    assert len(calc.channel) == len(g["channel"])
+    assert np.allclose(np.array(calc.channel)[:, :6], g["channel"][:, :6])
+    assert np.abs(np.array(calc.channel)[:, 6] - g["channel"][:, 6]).max() < 1e-9
+    assert np.allclose(np.array(calc.basisStates), g["basisStates"])
+    assert np.array_equal(calc.index, g["index"])
+    assert calc.originalPairStateIndex == int(g["originalPairStateIndex"])
+    d = calc.matDiagonal.diagonal()
+    assert np.abs(d - g["matDiagonal"]).max() <= 1e-9 * max(1.0, np.abs(d).max())
+    for o, m in enumerate(calc.matR):
+        assert m.nnz == int(g["matR%d_nnz" % o]), o
+        ref = g["matR%d_probe" % o]
+        got = m.dot(g["probes"])
+        assert np.abs(got - ref).max() <= 1e-8 * np.abs(ref).max(), o
+        if "matR%d_rows" % o in g:
+            dense = np.zeros(m.shape)
+            dense[g["matR%d_rows" % o], g["matR%d_cols" % o]] = g["matR%d_vals" % o]
+            assert np.abs(m.toarray() - dense).max() <= 1e-8 * np.abs(dense).max()
+    for o, c in enumerate(calc.coupling):
+        assert c.nnz == int(g["coupling%d_nnz" % o])
+        assert abs(abs(c).sum() - float(g["coupling%d_sumabs" % o])) <= 1e-8 * float(g["coupling%d_sumabs" % o])
+
+
+def test_phi_nonzero_rejected():
+    import arc_b200
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 60, 0, .5, 60, 0, .5, .5, .5)
+    with pytest.raises(NotImplementedError):
+        calc.defineBasis(0.3, 0.2, 1, 2, 1e9)
