@@ -7,14 +7,16 @@
 //   per column c of a panel (3 cluster barriers):
 //     phase 1  lazy update of column c with the panel's (V, W); norm partials
 //     phase 2  v = Householder vector; symmetric mat-vec  w = A v  on the lower
-//              triangle: each 32x32 tile is read ONCE (coalesced, lane <-> row) and used
-//              for both A_IJ v_J (registers) and A_IJ^T v_I (via a padded shared-memory
-//              transpose, lane <-> column) -- algorithmic HBM bytes 4 N^3 / 3 per matrix;
-//              panel dot products W^T v, V^T v ride along
+//              triangle: each 32x32 tile is read ONCE (coalesced, lane <-> row, next tile
+//              prefetched into registers) and used for both A_IJ v_J (registers) and
+//              A_IJ^T v_I (padded shared-memory transpose, lane <-> column, reduced across
+//              block rows with FP64 reductions in L2) -- algorithmic HBM bytes 4 N^3 / 3
+//              per matrix; panel dot products W^T v, V^T v ride along
 //     phase 3  w -= V (W^T v) + W (V^T v); w *= tau; partial w.v
 //     phase 4  w -= (tau/2)(w.v) v  -> column of W
 //   per panel: trailing update A -= V W^T + W V^T with FP64 tensor-core DMMA tiles
-//   (mma.sync.m8n8k4.f64), fragments read straight from the 32-wide panels.
+//   (mma.sync.m8n8k4.f64); the panel rows of block column J are staged in shared memory
+//   once per CTA (conflict-free stride 36), A fragments come from the warp's own rows.
 // Vectors are exchanged through L2 (ld.global.cg) between cluster barriers.
 #include <cooperative_groups.h>
 #include "eig.cuh"
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
     double *__restrict__ A = slot + a.oA;
     double *__restrict__ Wp = slot + a.oWp;       // [Npad][32] row-major
     double *__restrict__ Vp = slot + a.oVp;
-    double *__restrict__ trans = slot + a.oTrans; // [NB][Npad]
+    double *__restrict__ wtr = slot + a.oTrans;   // [Npad] L2-reduced transposed part of the mat-vec
     double *__restrict__ wdir = slot + a.oWdir;
     double *__restrict__ dd = slot + a.oD;
     double *__restrict__ ee = slot + a.oE;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             double nrm = 0.0;
             for (int I = first_owned(c / 32); I < NB; I += nW) {
                 const int r = 32 * I + lane;
+                wtr[r] = 0.0;
                 if (r >= c && r < N) {
                     double av = __ldcg(&A[r + (size_t)c * lda]);
                     const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
@@ -162,51 +165,77 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
 
             const int Jmin = (c + 1) / 32;
             double t1acc = 0.0, t2acc = 0.0;
-            for (int I = first_owned(Jmin); I < NB; I += nW) {
-                const int r = 32 * I + lane;
-                double vI[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) vI[q] = v[32 * I + q];
-                if (r >= c + 1) Vp[(size_t)r * 32 + i] = v[r];
-                if (lane < i) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const size_t rr = (size_t)(32 * I + q) * 32 + lane;
-                        t1acc += Wp[rr] * vI[q];
-                        t2acc += Vp[rr] * vI[q];
-                    }
-                }
+            {
+                // flattened tile sequence of this warp: (I, J), I owned, J = Jmin..I, with the
+                // next tile's 32 loads in flight while the current tile is consumed
+                int I = first_owned(Jmin), J = Jmin;
+                bool have = I < NB;
+                double ta[32], tb[32];
                 double wr = 0.0;
-                for (int J = Jmin; J <= I; ++J) {
-                    double areg[32];
-                    const double *ap = &A[r + (size_t)(32 * J) * lda];
+                auto load_tile = [&](double(&t)[32], int I_, int J_) {
+                    const double *ap = &A[(32 * I_ + lane) + (size_t)(32 * J_) * lda];
 #pragma unroll
-                    for (int cc = 0; cc < 32; ++cc) areg[cc] = __ldcg(ap + (size_t)cc * lda);
-                    const double *vJ = &v[32 * J];
-                    if (J < I) {
+                    for (int cc = 0; cc < 32; ++cc) t[cc] = __ldcg(ap + (size_t)cc * lda);
+                };
+                auto consume = [&](const double(&t)[32], int I_, int J_) {
+                    const int r = 32 * I_ + lane;
+                    if (J_ == Jmin) {
+                        // once per block row: V panel column and panel dot products
+                        if (r >= c + 1) Vp[(size_t)r * 32 + i] = v[r];
+                        if (lane < i) {
+#pragma unroll 8
+                            for (int q = 0; q < 32; ++q) {
+                                const size_t rr = (size_t)(32 * I_ + q) * 32 + lane;
+                                const double vq = v[32 * I_ + q];
+                                t1acc += Wp[rr] * vq;
+                                t2acc += Vp[rr] * vq;
+                            }
+                        }
+                    }
+                    const double *vJ = &v[32 * J_];
+                    const double vr = v[r];
+                    if (J_ < I_) {
 #pragma unroll
-                        for (int cc = 0; cc < 32; ++cc) wr += areg[cc] * vJ[cc];
+                        for (int cc = 0; cc < 32; ++cc) {
+                            wr += t[cc] * vJ[cc];
+                            mytile[cc * TPAD + lane] = t[cc] * vr;
+                        }
                     } else {
 #pragma unroll
-                        for (int cc = 0; cc < 32; ++cc)
-                            if (cc <= lane) wr += areg[cc] * vJ[cc];
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc) mytile[cc * TPAD + lane] = areg[cc];
-                    __syncwarp();
-                    double s = 0.0;
-                    if (J < I) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) s += mytile[lane * TPAD + q] * vI[q];
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q)
-                            if (q > lane) s += mytile[lane * TPAD + q] * vI[q];
+                        for (int cc = 0; cc < 32; ++cc) {
+                            if (cc <= lane) wr += t[cc] * vJ[cc];
+                            mytile[cc * TPAD + lane] = (lane > cc) ? t[cc] * vr : 0.0;
+                        }
                     }
                     __syncwarp();
-                    __stcg(&trans[(size_t)I * lda + 32 * J + lane], s);
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 32; q += 2) {
+                        s0 += mytile[lane * TPAD + q];
+                        s1 += mytile[lane * TPAD + q + 1];
+                    }
+                    __syncwarp();
+                    // A_IJ^T v_I contributes to w[32J + lane]: reduced in L2 (fire and forget)
+                    atomicAdd(&wtr[32 * J_ + lane], s0 + s1);
+                    if (J_ == I_) { wdir[r] = wr; wr = 0.0; }
+                };
+                auto advance = [&](int &I_, int &J_) {
+                    if (++J_ > I_) { I_ += nW; J_ = Jmin; }
+                    return I_ < NB;
+                };
+                if (have) load_tile(ta, I, J);
+                while (have) {
+                    int nI = I, nJ = J;
+                    bool hn = advance(nI, nJ);
+                    if (hn) load_tile(tb, nI, nJ);
+                    consume(ta, I, J);
+                    I = nI; J = nJ; have = hn;
+                    if (!have) break;
+                    hn = advance(nI, nJ);
+                    if (hn) load_tile(ta, nI, nJ);
+                    consume(tb, I, J);
+                    I = nI; J = nJ; have = hn;
                 }
-                wdir[r] = wr;
             }
             sred[wid][lane] = t1acc;
             sred[wid][32 + lane] = t2acc;
@@ -234,8 +263,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             for (int I = first_owned(Jmin); I < NB; I += nW) {
                 const int r = 32 * I + lane;
                 if (r >= c + 1 && r < N) {
-                    double w = wdir[r];
-                    for (int II = I; II < NB; ++II) w += __ldcg(&trans[(size_t)II * lda + r]);
+                    double w = wdir[r] + __ldcg(&wtr[r]);
                     const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
                     for (int j = 0; j < i; ++j) w -= vr[j] * t1s[j] + wr[j] * t2s[j];
                     w *= tau;
@@ -246,14 +274,13 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             // every CTA recomputes W(c+1, i) (the next pivot-row entry) redundantly
             double wpiv = 0.0;
             if (wid == 0) {
-                const int r = c + 1, I = r / 32;
+                const int r = c + 1;
                 double part = 0.0;
-                for (int II = I + lane; II < NB; II += 32) part += __ldcg(&trans[(size_t)II * lda + r]);
                 if (lane < i)
                     part -= __ldcg(&Vp[(size_t)r * 32 + lane]) * t1s[lane]
                             + __ldcg(&Wp[(size_t)r * 32 + lane]) * t2s[lane];
                 part = warp_sum(part);
-                wpiv = (part + __ldcg(&wdir[r])) * tau;
+                wpiv = (part + __ldcg(&wdir[r]) + __ldcg(&wtr[r])) * tau;
             }
             pacc = warp_sum(pacc);
             if (lane == 0) sred[wid][0] = pacc;
@@ -288,28 +315,34 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
 
         // ---------------- trailing update: A -= V W^T + W V^T  (DMMA) --------------
         const int Jt = k0 / 32 + 1;
-        for (int I = first_owned(Jt); I < NB; I += nW) {
-            for (int mt = 0; mt < 4; ++mt) {
-                const int ar = 32 * I + 8 * mt + grp;
-                double fv[8], fw[8];
+        double(*BsW)[36] = reinterpret_cast<double(*)[36]>(tile);            // [n][k], stride 36:
+        double(*BsV)[36] = reinterpret_cast<double(*)[36]>(tile + 32 * 36);  // conflict-free frags
+        for (int J = Jt; J < NB; ++J) {
+            __syncthreads();
+            for (int t = tid; t < 1024; t += SY_THREADS) {
+                BsW[t >> 5][t & 31] = __ldcg(&Wp[(size_t)(32 * J) * 32 + t]);
+                BsV[t >> 5][t & 31] = __ldcg(&Vp[(size_t)(32 * J) * 32 + t]);
+            }
+            __syncthreads();
+            for (int I = first_owned(J); I < NB; I += nW) {
+#pragma unroll 1
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int ar = 32 * I + 8 * mt + grp;
+                    double fv[8], fw[8];
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    fv[ks] = -Vp[(size_t)ar * 32 + 4 * ks + tig];
-                    fw[ks] = -Wp[(size_t)ar * 32 + 4 * ks + tig];
-                }
-                for (int J = Jt; J <= I; ++J) {
+                    for (int ks = 0; ks < 8; ++ks) {
+                        fv[ks] = -Vp[(size_t)ar * 32 + 4 * ks + tig];
+                        fw[ks] = -Wp[(size_t)ar * 32 + 4 * ks + tig];
+                    }
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        const int bc = 32 * J + 8 * nt + grp;   // column index held as B row
                         const int cc = 32 * J + 8 * nt + 2 * tig;
                         double *cp = &A[ar + (size_t)cc * lda];
                         double c0 = __ldcg(cp), c1 = __ldcg(cp + lda);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
-                            const double bw = __ldcg(&Wp[(size_t)bc * 32 + 4 * ks + tig]);
-                            const double bv = __ldcg(&Vp[(size_t)bc * 32 + 4 * ks + tig]);
-                            dmma8x8x4(c0, c1, fv[ks], bw);
-                            dmma8x8x4(c0, c1, fw[ks], bv);
+                            dmma8x8x4(c0, c1, fv[ks], BsW[8 * nt + grp][4 * ks + tig]);
+                            dmma8x8x4(c0, c1, fw[ks], BsV[8 * nt + grp][4 * ks + tig]);
                         }
                         cp[0] = c0;
                         cp[lda] = c1;

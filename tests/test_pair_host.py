@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.oracle_radial import patch_atom_with_oracle
+from oracle.host_radial import patch_atom_with_oracle
 
 
 def _build(g):
