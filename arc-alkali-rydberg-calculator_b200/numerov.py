@@ -29,7 +29,7 @@ def NumerovWavefunction(innerLimit, outerLimit, step, init1, init2, l, s, j,
 def NumerovBack(innerLimit, outerLimit, kfun, step, init1, init2):
     """Signature of alkali_atom_functions.py:3939.  The reference's Python twin takes an
     arbitrary callable kfun(x); a GPU kernel cannot call back into Python, and the
-    Python twin is not the oracle (it differs from the C path by 6e-5),
+    Python twin is not the parity target (it differs from the C path by 6e-5),
     so this entry point accepts only callables that carry the 12 physical parameters of
     the C path as attribute `arcb200_params` = (l, s, j, stateEnergy, alphaC, alpha, Z,
     a1, a2, a3, a4, rc, mu) and routes them to the CUDA kernel.  Returns (r, psi)."""

@@ -1,0 +1,68 @@
+"""world_size-2 gloo test of the sweep sharding + result gather (the N>1 host path)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from arc_b200 import sweep
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, npoints, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert sweep.dist_info() == (rank, world)
+        lo, hi = sweep.shard_bounds(npoints, rank, world)
+        # every rank "solves" its own shard: row p holds f(p)
+        local = torch.stack([torch.arange(4, dtype=torch.float64) + 10.0 * p for p in range(lo, hi)]) \
+            if hi > lo else torch.zeros((0, 4), dtype=torch.float64)
+        full = sweep.gather_rows(local, npoints)
+        li = torch.arange(lo, hi, dtype=torch.int32).reshape(-1, 1, 1).expand(-1, 2, 3).contiguous()
+        fi = sweep.gather_rows(li, npoints)
+        q.put((rank, full.numpy(), fi.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(npoints):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, npoints, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return outs
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 600, 1000, 4096):
+        for w in (1, 2, 3, 8):
+            b = [sweep.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_gather_rows_gloo_world2_ragged():
+    for npoints in (7, 1):
+        want = np.stack([np.arange(4.0) + 10.0 * p for p in range(npoints)])
+        for rank, full, fi in _run(npoints):
+            assert full.shape == (npoints, 4)
+            assert np.array_equal(full, want)
+            assert np.array_equal(fi[:, 0, 0], np.arange(npoints))

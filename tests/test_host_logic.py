@@ -1,0 +1,115 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU): angular algebra,
+energies, Stark basis / matrix assembly, result containers -- against golden vectors frozen
+from the live reference (tools/gen_golden.py)."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle.host_radial import patch_atom_with_oracle
+
+
+@pytest.fixture(scope="module")
+def ang(gold_dir):
+    return json.load(open(os.path.join(gold_dir, "angular_golden.json")))
+
+
+def test_wigner_symbols(ang):
+    from arc_b200 import CG, Wigner3j, Wigner6j
+    for r in ang["CG"]:
+        assert abs(CG(*r[:6]) - r[6]) < 1e-13
+    for r in ang["w3j"]:
+        assert abs(Wigner3j(*r[:6]) - r[6]) < 1e-13
+    for r in ang["w6j"]:
+        l, s, j, j1, c, l1 = r[:6]
+        want = r[6]
+        got = Wigner6j(l, s, j, j1, c, l1)
+        if l1 - l == 2:            # the reference's shipped 6j table is empty for l1 = l+2
+            assert want == 0.0
+        else:
+            assert abs(got - want) < 1e-13
+
+
+def test_wigner_d_matrices(ang):
+    from arc_b200 import WignerDmatrix
+    for d in ang["wignerD"]:
+        m = WignerDmatrix(d["theta"], d["phi"]).get(d["j"])
+        ref = np.array(d["re"]) + 1j * np.array(d["im"])
+        assert np.abs(m - ref).max() < 1e-13
+    assert np.array_equal(WignerDmatrix(0, 0).get(1.5), np.eye(4))
+
+
+def test_efield_angular_and_zeeman(ang):
+    import arc_b200
+    from arc_b200.stark import efield_angular
+    for r in ang["efield"]:
+        assert abs(efield_angular(*r[:6], s=r[6]) - r[7]) < 1e-13
+    a = arc_b200.Rubidium()
+    for r in ang["zeeman"]:
+        v = a.getZeemanEnergyShift(r[0], r[1], r[2], r[3], s=r[4])
+        assert abs(v - r[5]) <= 1e-13 * max(abs(r[5]), 1e-30)
+
+
+def test_energies_match_reference(gold_dir):
+    import arc_b200
+    g = json.load(open(os.path.join(gold_dir, "radial_golden.json")))["atoms"]
+    for cls in g:
+        a = getattr(arc_b200, cls)()
+        for n, l, j, E in g[cls]["energies_eV"]:
+            assert a.getEnergy(n, l, j) == E
+    d = json.load(open(os.path.join(gold_dir, "divalent_golden.json")))
+    sr = arc_b200.Strontium88()
+    for n, l, j, s, E in d["energies_eV"]:
+        assert sr.getEnergy(n, l, j, s=s) == E
+    with pytest.raises(ValueError):
+        sr.getEnergy(50, 1, 1)            # spin must be explicit (div:322-327)
+    with pytest.raises(ValueError):
+        arc_b200.Rubidium().getEnergy(5, 5, 5.5)
+
+
+def test_stark_define_basis_host_logic(gold_dir):
+    """basis order, mat1 (incl. Zeeman), mat2 pattern and values; radial elements from the
+    oracle so this runs without a GPU."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "stark_small_bz_golden.npz"))
+    calc = arc_b200.StarkMap(patch_atom_with_oracle(arc_b200.Rubidium()))
+    a = g["args"]
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]),
+                     Bz=float(g["Bz"]))
+    assert np.allclose(np.array(calc.basisStates), g["basisStates"])
+    assert calc.indexOfCoupledState == int(g["indexOfCoupledState"])
+    assert np.abs(np.diag(calc.mat1) - g["mat1_diag"]).max() <= 1e-12 * np.abs(g["mat1_diag"]).max()
+    N = len(g["mat1_diag"])
+    m2 = np.zeros((N, N))
+    m2[g["mat2_rows"], g["mat2_cols"]] = g["mat2_vals"]
+    assert np.array_equal(calc.mat2 != 0, m2 != 0)
+    assert np.abs(calc.mat2 - m2).max() <= 1e-10 * np.abs(m2).max()
+    assert np.array_equal(calc.mat2, calc.mat2.T)
+
+
+def test_composition_view_and_pickle():
+    from arc_b200.stark import CompositionView
+    c = np.array([[[0.9, -0.3, 0.0], [1.0, 0.0, 0.0]]])
+    i = np.array([[[4, 2, -1], [7, -1, -1]]], dtype=np.int32)
+    v = CompositionView(c, i)
+    assert len(v) == 1
+    assert v[0][0] == [[0.9, 4], [-0.3, 2]] and v[0][1] == [[1.0, 7]]
+    assert v[0][1][0][1] == 7                       # the access pattern of pair:4766-4771
+    v2 = pickle.loads(pickle.dumps(v))
+    assert v2[0] == v[0]
+    import arc_b200
+    atom = pickle.loads(pickle.dumps(arc_b200.Rubidium()))       # saveCalculation-style
+    assert atom.getEnergy(60, 0, .5) == arc_b200.Rubidium().getEnergy(60, 0, .5)
+
+
+def test_selection_rules_return_zero_without_compute():
+    import arc_b200
+    a = arc_b200.Rubidium()
+    assert a.getRadialMatrixElement(30, 0, .5, 31, 2, 1.5) == 0
+    assert a.getQuadrupoleMatrixElement(30, 0, .5, 31, 3, 2.5) == 0
+    assert a.getRadialCoupling(30, 0, .5, 31, 4, 3.5) == 0
+    # literature value (rubidium_literature_dme.csv) is returned without any computation
+    assert a.getRadialMatrixElement(5, 0, .5, 5, 1, .5) == a._lit[(5, 0, 1, 5, 1, 1)][0]
+    assert a.gpu_kernel_launches == 0
