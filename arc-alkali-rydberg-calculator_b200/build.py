@@ -40,7 +40,8 @@ def needs_build():
 
 
 def build_lib(force=False, verbose=False):
-    if not force and not needs_build():
+    extra = os.environ.get("ARCB200_NVCC_EXTRA", "").split()
+    if not force and not needs_build() and not extra:
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -49,7 +50,7 @@ def build_lib(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:

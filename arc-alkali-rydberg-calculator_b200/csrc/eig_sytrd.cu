@@ -23,6 +23,14 @@
 
 namespace cg = cooperative_groups;
 
+#ifdef SYTRD_PROFILE
+#define PROF_DECL long long prof_t[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long prof_last = clock64();
+#define PROF(k) { long long now_ = clock64(); prof_t[k] += now_ - prof_last; prof_last = now_; }
+#else
+#define PROF_DECL
+#define PROF(k)
+#endif
+
 namespace {
 
 constexpr int SY_WARPS = 8;
@@ -43,6 +51,22 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
+// sum_j V(r,j)*a[j] + W(r,j)*b[j] over the 32 panel columns (unused columns are zero).
+// Panels are column-major [32][Npad]: lane <-> row, so each of the 64 loads is one
+// coalesced 256-byte warp request and all of them are in flight together.
+__device__ __forceinline__ double panel_row_dot(const double *__restrict__ vcol,
+                                                const double *__restrict__ wcol, int ld,
+                                                const double *a, const double *b)
+{
+    double x[32], y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { x[j] = vcol[(size_t)j * ld]; y[j] = wcol[(size_t)j * ld]; }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s0 += x[j] * a[j]; s1 += y[j] * b[j]; }
+    return s0 + s1;
+}
+
 template <bool CL>
 __device__ __forceinline__ void group_sync(cg::cluster_group &cl)
 {
@@ -59,10 +83,9 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
     const int N = a.N, lda = a.Npad, NB = a.NB;
     double *slot = a.base + (size_t)mat * a.slot;
     double *__restrict__ A = slot + a.oA;
-    double *__restrict__ Wp = slot + a.oWp;       // [Npad][32] row-major
+    double *__restrict__ Wp = slot + a.oWp;       // [32][Npad] column-major panels
     double *__restrict__ Vp = slot + a.oVp;
     double *__restrict__ wtr = slot + a.oTrans;   // [Npad] L2-reduced transposed part of the mat-vec
-    double *__restrict__ wdir = slot + a.oWdir;
     double *__restrict__ dd = slot + a.oD;
     double *__restrict__ ee = slot + a.oE;
     double *__restrict__ tt = slot + a.oTau;
@@ -72,7 +95,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
     double *v = smem;                              // [Npad]
     double *tile = smem + lda;                     // [SY_WARPS][32*TPAD]
     __shared__ double sred[SY_WARPS][64];
-    __shared__ double pv[32], pw[32], t1s[32], t2s[32];
+    __shared__ __align__(32) double pv[32], pw[32], t1s[32], t2s[32];
     __shared__ double sbc[4];
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -84,14 +107,16 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
     auto first_owned = [&](int I0) { return I0 + ((gw - I0 % nW) + nW) % nW; };
 
     double pw_last = 0.0;    // W(c, i-1) computed redundantly by every CTA
+    PROF_DECL
 
     for (int k0 = 0; k0 < N; k0 += 32) {
         const int k1 = min(k0 + 32, N);
         // zero the panels for the rows this warp owns
         for (int I = first_owned(k0 / 32); I < NB; I += nW) {
+#pragma unroll 8
             for (int q = 0; q < 32; ++q) {
-                Wp[(size_t)(32 * I + q) * 32 + lane] = 0.0;
-                Vp[(size_t)(32 * I + q) * 32 + lane] = 0.0;
+                Wp[(size_t)q * lda + 32 * I + lane] = 0.0;
+                Vp[(size_t)q * lda + 32 * I + lane] = 0.0;
             }
         }
         __syncwarp();
@@ -99,12 +124,19 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
         for (int c = k0; c < k1; ++c) {
             const int i = c - k0;
             // pivot-row entries V(c, j), W(c, j), j < i
-            if (wid == 0 && lane < i) {
-                pv[lane] = (lane == i - 1) ? 1.0 : __ldcg(&Vp[(size_t)c * 32 + lane]);
-                pw[lane] = (lane == i - 1) ? pw_last : __ldcg(&Wp[(size_t)c * 32 + lane]);
+            if (wid == 0) {
+                // entries j >= i are zero so that the row updates can run over all 32 columns
+                double a_ = 0.0, b_ = 0.0;
+                if (lane < i) {
+                    a_ = (lane == i - 1) ? 1.0 : __ldcg(&Vp[(size_t)lane * lda + c]);
+                    b_ = (lane == i - 1) ? pw_last : __ldcg(&Wp[(size_t)lane * lda + c]);
+                }
+                pv[lane] = a_;
+                pw[lane] = b_;
             }
             __syncthreads();
 
+            PROF(0)
             // ---------------- phase 1: lazy update of column c --------------------
             double nrm = 0.0;
             for (int I = first_owned(c / 32); I < NB; I += nW) {
@@ -112,8 +144,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 wtr[r] = 0.0;
                 if (r >= c && r < N) {
                     double av = __ldcg(&A[r + (size_t)c * lda]);
-                    const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
-                    for (int j = 0; j < i; ++j) av -= vr[j] * pw[j] + wr[j] * pv[j];
+                    av -= panel_row_dot(Vp + r, Wp + r, lda, pw, pv);
                     A[r + (size_t)c * lda] = av;
                     if (r >= c + 2) nrm += av * av;
                     if (r == c) dd[c] = av;
@@ -129,7 +160,9 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 for (int q = 0; q < SY_WARPS; ++q) s += sred[q][0];
                 scr[8 + rank] = s;
             }
+            PROF(1)
             group_sync<CL>(cluster);                                   // ---- B1
+            PROF(2)
 
             double alpha = __ldcg(&scr[0]);
             double xn2 = 0.0;
@@ -147,7 +180,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 // H = I: V column = unit vector (never multiplied by anything but W=0)
                 for (int I = first_owned((c + 1) / 32); I < NB; I += nW) {
                     const int r = 32 * I + lane;
-                    if (r == c + 1) Vp[(size_t)r * 32 + i] = 1.0;
+                    if (r == c + 1) Vp[(size_t)i * lda + r] = 1.0;
                 }
                 pw_last = 0.0;
                 __syncthreads();
@@ -163,47 +196,82 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             }
             __syncthreads();
 
+            PROF(3)
             const int Jmin = (c + 1) / 32;
             double t1acc = 0.0, t2acc = 0.0;
+            // V panel column + panel dot products W^T v, V^T v for the block rows this warp
+            // owns: coalesced loads (lane <-> row), products transposed through shared memory
+            // so that lane j ends up with the sum over the 32 rows (like the symv tiles)
+            for (int I = first_owned(Jmin); I < NB; I += nW) {
+                const int r = 32 * I + lane;
+                const double vr_ = v[r];
+                if (r >= c + 1) Vp[(size_t)i * lda + r] = vr_;
+                if (i == 0) continue;
+                double x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = Wp[(size_t)j * lda + r];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = x[j] * vr_;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = Vp[(size_t)j * lda + r];
+                {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
+                    t1acc += s0 + s1;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = x[j] * vr_;
+                __syncwarp();
+                {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
+                    t2acc += s0 + s1;
+                }
+                __syncwarp();
+            }
+            if (lane >= i) { t1acc = 0.0; t2acc = 0.0; }
+            PROF(4)
             {
-                // flattened tile sequence of this warp: (I, J), I owned, J = Jmin..I, with the
-                // next tile's 32 loads in flight while the current tile is consumed
-                int I = first_owned(Jmin), J = Jmin;
-                bool have = I < NB;
+                // symmetric mat-vec over the lower-triangular tiles (I >= J >= Jmin), dealt to
+                // the cluster's warps in contiguous, equally sized chunks of the J-major tile
+                // list (balanced; neighbouring warps stream neighbouring memory).  Both halves
+                // of the product are reduced in L2:  w[32I..] += A_IJ v_J,  w[32J..] += A_IJ^T v_I.
+                const int m = NB - Jmin;
+                const int T = m * (m + 1) / 2;
+                const int t0 = (int)(((long long)T * gw) / nW), t1 = (int)(((long long)T * (gw + 1)) / nW);
+                int ntile = t1 - t0;
+                // tile t0 -> (I, J): column jj holds m - jj tiles
+                int jj = (int)(((2.0 * m + 1.0) - sqrt((2.0 * m + 1.0) * (2.0 * m + 1.0) - 8.0 * t0)) * 0.5);
+                while (jj > 0 && jj * m - jj * (jj - 1) / 2 > t0) --jj;
+                while ((jj + 1) * m - (jj + 1) * jj / 2 <= t0) ++jj;
+                int J = Jmin + jj, I = J + (t0 - (jj * m - jj * (jj - 1) / 2));
                 double ta[32], tb[32];
-                double wr = 0.0;
+                double sacc = 0.0;
                 auto load_tile = [&](double(&t)[32], int I_, int J_) {
                     const double *ap = &A[(32 * I_ + lane) + (size_t)(32 * J_) * lda];
 #pragma unroll
                     for (int cc = 0; cc < 32; ++cc) t[cc] = __ldcg(ap + (size_t)cc * lda);
                 };
-                auto consume = [&](const double(&t)[32], int I_, int J_) {
-                    const int r = 32 * I_ + lane;
-                    if (J_ == Jmin) {
-                        // once per block row: V panel column and panel dot products
-                        if (r >= c + 1) Vp[(size_t)r * 32 + i] = v[r];
-                        if (lane < i) {
-#pragma unroll 8
-                            for (int q = 0; q < 32; ++q) {
-                                const size_t rr = (size_t)(32 * I_ + q) * 32 + lane;
-                                const double vq = v[32 * I_ + q];
-                                t1acc += Wp[rr] * vq;
-                                t2acc += Vp[rr] * vq;
-                            }
-                        }
-                    }
+                auto consume = [&](const double(&t)[32], int I_, int J_, bool lastOfJ) {
                     const double *vJ = &v[32 * J_];
-                    const double vr = v[r];
+                    const double vr = v[32 * I_ + lane];
+                    double wr0 = 0.0, wr1 = 0.0;
                     if (J_ < I_) {
 #pragma unroll
-                        for (int cc = 0; cc < 32; ++cc) {
-                            wr += t[cc] * vJ[cc];
+                        for (int cc = 0; cc < 32; cc += 2) {
+                            wr0 += t[cc] * vJ[cc];
+                            wr1 += t[cc + 1] * vJ[cc + 1];
                             mytile[cc * TPAD + lane] = t[cc] * vr;
+                            mytile[(cc + 1) * TPAD + lane] = t[cc + 1] * vr;
                         }
                     } else {
 #pragma unroll
                         for (int cc = 0; cc < 32; ++cc) {
-                            if (cc <= lane) wr += t[cc] * vJ[cc];
+                            if (cc <= lane) wr0 += t[cc] * vJ[cc];
                             mytile[cc * TPAD + lane] = (lane > cc) ? t[cc] * vr : 0.0;
                         }
                     }
@@ -215,28 +283,28 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                         s1 += mytile[lane * TPAD + q + 1];
                     }
                     __syncwarp();
-                    // A_IJ^T v_I contributes to w[32J + lane]: reduced in L2 (fire and forget)
-                    atomicAdd(&wtr[32 * J_ + lane], s0 + s1);
-                    if (J_ == I_) { wdir[r] = wr; wr = 0.0; }
+                    atomicAdd(&wtr[32 * I_ + lane], wr0 + wr1);
+                    sacc += s0 + s1;
+                    if (lastOfJ) { atomicAdd(&wtr[32 * J_ + lane], sacc); sacc = 0.0; }
                 };
                 auto advance = [&](int &I_, int &J_) {
-                    if (++J_ > I_) { I_ += nW; J_ = Jmin; }
-                    return I_ < NB;
+                    if (++I_ >= NB) { ++J_; I_ = J_; }
                 };
-                if (have) load_tile(ta, I, J);
-                while (have) {
+                if (ntile > 0) load_tile(ta, I, J);
+                while (ntile > 0) {
                     int nI = I, nJ = J;
-                    bool hn = advance(nI, nJ);
-                    if (hn) load_tile(tb, nI, nJ);
-                    consume(ta, I, J);
-                    I = nI; J = nJ; have = hn;
-                    if (!have) break;
-                    hn = advance(nI, nJ);
-                    if (hn) load_tile(ta, nI, nJ);
-                    consume(tb, I, J);
-                    I = nI; J = nJ; have = hn;
+                    advance(nI, nJ);
+                    if (ntile > 1) load_tile(tb, nI, nJ);
+                    consume(ta, I, J, ntile == 1 || nJ != J);
+                    I = nI; J = nJ; --ntile;
+                    if (ntile == 0) break;
+                    advance(nI, nJ);
+                    if (ntile > 1) load_tile(ta, nI, nJ);
+                    consume(tb, I, J, ntile == 1 || nJ != J);
+                    I = nI; J = nJ; --ntile;
                 }
             }
+            PROF(5)
             sred[wid][lane] = t1acc;
             sred[wid][32 + lane] = t2acc;
             __syncthreads();
@@ -247,6 +315,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 __stcg(&scr[64 + 64 * rank + 32 + lane], s2);
             }
             group_sync<CL>(cluster);                                   // ---- B2
+            PROF(6)
 
             // ---------------- phase 3 --------------------------------------------
             if (wid == 0) {
@@ -263,12 +332,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             for (int I = first_owned(Jmin); I < NB; I += nW) {
                 const int r = 32 * I + lane;
                 if (r >= c + 1 && r < N) {
-                    double w = wdir[r] + __ldcg(&wtr[r]);
-                    const double *vr = &Vp[(size_t)r * 32], *wr = &Wp[(size_t)r * 32];
-                    for (int j = 0; j < i; ++j) w -= vr[j] * t1s[j] + wr[j] * t2s[j];
+                    double w = __ldcg(&wtr[r]);
+                    w -= panel_row_dot(Vp + r, Wp + r, lda, t1s, t2s);
                     w *= tau;
                     pacc += w * v[r];
-                    Wp[(size_t)r * 32 + i] = w;
+                    Wp[(size_t)i * lda + r] = w;
                 }
             }
             // every CTA recomputes W(c+1, i) (the next pivot-row entry) redundantly
@@ -277,10 +345,10 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 const int r = c + 1;
                 double part = 0.0;
                 if (lane < i)
-                    part -= __ldcg(&Vp[(size_t)r * 32 + lane]) * t1s[lane]
-                            + __ldcg(&Wp[(size_t)r * 32 + lane]) * t2s[lane];
+                    part -= __ldcg(&Vp[(size_t)lane * lda + r]) * t1s[lane]
+                            + __ldcg(&Wp[(size_t)lane * lda + r]) * t2s[lane];
                 part = warp_sum(part);
-                wpiv = (part + __ldcg(&wdir[r]) + __ldcg(&wtr[r])) * tau;
+                wpiv = (part + __ldcg(&wtr[r])) * tau;
             }
             pacc = warp_sum(pacc);
             if (lane == 0) sred[wid][0] = pacc;
@@ -290,7 +358,9 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 for (int q = 0; q < SY_WARPS; ++q) s += sred[q][0];
                 __stcg(&scr[32 + rank], s);
             }
+            PROF(7)
             group_sync<CL>(cluster);                                   // ---- B3
+            PROF(8)
 
             // ---------------- phase 4 --------------------------------------------
             double p = 0.0;
@@ -299,7 +369,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             for (int I = first_owned(Jmin); I < NB; I += nW) {
                 const int r = 32 * I + lane;
                 if (r >= c + 1 && r < N) {
-                    Wp[(size_t)r * 32 + i] += alpha2 * v[r];
+                    Wp[(size_t)i * lda + r] += alpha2 * v[r];
                     if (r >= c + 2) A[r + (size_t)c * lda] = v[r];
                 }
             }
@@ -308,6 +378,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
             }
             __syncthreads();
             pw_last = sbc[0];
+            PROF(9)
         }  // columns of the panel
 
         if (k0 + 32 >= N) break;
@@ -320,40 +391,63 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
         for (int J = Jt; J < NB; ++J) {
             __syncthreads();
             for (int t = tid; t < 1024; t += SY_THREADS) {
-                BsW[t >> 5][t & 31] = __ldcg(&Wp[(size_t)(32 * J) * 32 + t]);
-                BsV[t >> 5][t & 31] = __ldcg(&Vp[(size_t)(32 * J) * 32 + t]);
+                // t -> (k = t >> 5, n = t & 31): coalesced along the rows of block column J
+                BsW[t & 31][t >> 5] = __ldcg(&Wp[(size_t)(t >> 5) * lda + 32 * J + (t & 31)]);
+                BsV[t & 31][t >> 5] = __ldcg(&Vp[(size_t)(t >> 5) * lda + 32 * J + (t & 31)]);
             }
             __syncthreads();
             for (int I = first_owned(J); I < NB; I += nW) {
-#pragma unroll 1
-                for (int mt = 0; mt < 4; ++mt) {
-                    const int ar = 32 * I + 8 * mt + grp;
-                    double fv[8], fw[8];
+                // one 32x32 tile: all 32 C values and the 64 A fragments are requested up
+                // front (independent loads), then 256 DMMAs on 16 independent accumulators
+                const int ar0 = 32 * I + grp;
+                double *cp0 = &A[ar0 + (size_t)(32 * J + 2 * tig) * lda];
+                double c0[4][4], c1[4][4];
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        fv[ks] = -Vp[(size_t)ar * 32 + 4 * ks + tig];
-                        fw[ks] = -Wp[(size_t)ar * 32 + 4 * ks + tig];
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        c0[mt][nt] = __ldcg(cp0 + 8 * mt + (size_t)(8 * nt) * lda);
+                        c1[mt][nt] = __ldcg(cp0 + 8 * mt + (size_t)(8 * nt + 1) * lda);
+                    }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double fv[4], fw[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        fv[mt] = -Vp[(size_t)(4 * ks + tig) * lda + ar0 + 8 * mt];
+                        fw[mt] = -Wp[(size_t)(4 * ks + tig) * lda + ar0 + 8 * mt];
                     }
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        const int cc = 32 * J + 8 * nt + 2 * tig;
-                        double *cp = &A[ar + (size_t)cc * lda];
-                        double c0 = __ldcg(cp), c1 = __ldcg(cp + lda);
+                        const double bw = BsW[8 * nt + grp][4 * ks + tig];
+                        const double bv = BsV[8 * nt + grp][4 * ks + tig];
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            dmma8x8x4(c0, c1, fv[ks], BsW[8 * nt + grp][4 * ks + tig]);
-                            dmma8x8x4(c0, c1, fw[ks], BsV[8 * nt + grp][4 * ks + tig]);
+                        for (int mt = 0; mt < 4; ++mt) {
+                            dmma8x8x4(c0[mt][nt], c1[mt][nt], fv[mt], bw);
+                            dmma8x8x4(c0[mt][nt], c1[mt][nt], fw[mt], bv);
                         }
-                        cp[0] = c0;
-                        cp[lda] = c1;
                     }
                 }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        cp0[8 * mt + (size_t)(8 * nt) * lda] = c0[mt][nt];
+                        cp0[8 * mt + (size_t)(8 * nt + 1) * lda] = c1[mt][nt];
+                    }
             }
         }
+        PROF(10)
         // other CTAs read this CTA's panel rows as B fragments: nobody may start zeroing
         // the panels for the next block column before every CTA is done with them
         group_sync<CL>(cluster);
     }  // panels
+#ifdef SYTRD_PROFILE
+    if (mat == 0 && tid == 0) {
+        printf("sytrd prof rank %d: col-setup %lld ph1 %lld B1 %lld vload %lld dots %lld symv %lld B2wait %lld ph3 %lld B3wait %lld ph4 %lld update %lld (Mcycles)\n", rank,
+               prof_t[0] / 1000000, prof_t[1] / 1000000, prof_t[2] / 1000000, prof_t[3] / 1000000, prof_t[4] / 1000000, prof_t[5] / 1000000, prof_t[6] / 1000000, prof_t[7] / 1000000, prof_t[8] / 1000000, prof_t[9] / 1000000, prof_t[10] / 1000000);
+    }
+#endif
 }
 
 }  // namespace
