@@ -454,11 +454,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
 
 int eig_pick_cluster(int N, int nmat)
 {
-    // enough matrices to fill 148 SMs with one CTA each -> no cluster; otherwise spread
-    // each matrix over a cluster so the whole GPU streams.
+    // Measured on B200 (N=2363): 1 or 2 CTAs per matrix are the efficient shapes (4.2-4.4
+    // ms/matrix); clusters of 4/8 pay for barriers and short per-warp tile lists (8-10
+    // ms/matrix).  So: the smallest cluster that still occupies about half of the 148 SMs.
     int c = 1;
-    while (c < 8 && nmat * c * 2 <= 148 && N >= 64 * c) c *= 2;
-    if (N >= 4096 && c < 8) c = 8;
+    while (c < 8 && nmat * c < 74 && N >= 128 * c) c *= 2;
     return c;
 }
 

@@ -54,9 +54,12 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     lib = _lib.load()
     per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
     b = int(min(npoints, max(1, (0.6 * free) // per)))
-    # two waves of one cluster-per-matrix tridiagonalisation keep 148 SMs busy
-    cap = 592 if N <= 512 else (148 if N <= 1024 else (72 if N <= 4096 else 18))
-    return max(1, min(b, cap))
+    # one CTA (or a small cluster) per matrix: 148 matrices in flight fill the GPU
+    cap = 592 if N <= 512 else (296 if N <= 1024 else (148 if N <= 4096 else 18))
+    b = max(1, min(b, cap))
+    # equal chunks: a nearly empty tail pass costs a full sweep latency
+    nchunks = -(-npoints // b)
+    return -(-npoints // nchunks)
 
 
 class SweepResult:
