@@ -64,7 +64,10 @@ struct EigSlots {
 // stage 1: A (lower, column-major, lda=Npad) -> d, e, Householder vectors in A, tau
 int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *launches);
 // stage 2: (d, e) -> eigenvalues (ascending, in oLam) and eigenvectors of T in Q1
-int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
+// sel_k > 0: only the sel_k eigenpairs nearest sigma are needed; their first index per
+// matrix is written to d_sel0 and only those eigenvector columns of Q1 are valid.
+int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches, int sel_k = 0,
+              double sigma = 0.0, int32_t *d_sel0 = nullptr);
 // stage 3: Z = Q_house * Q1[:, sel0 : sel0+nsel]  (in place on Q1 columns)
 int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
               int *launches);

@@ -29,7 +29,8 @@ struct DcArgs {
     int32_t *ibase; size_t islot;
     size_t oQa, oQb, oU, oD, oE, oLam, oAux;
     size_t oPerm, oIdx;
-    int out_lo_dummy;
+    const int32_t *win0;     // per matrix first selected final position (level 0 only)
+    int wink;                // number of selected eigenpairs (0 = all)
 };
 
 // per-slot aux double arrays (each Npad long), offsets inside oAux
@@ -484,10 +485,9 @@ __global__ void __launch_bounds__(128) zhat_kernel(DcArgs a, int level, int nmat
     zhat[i] = copysign(sqrt(fabs(w)), z[i]);
 }
 
-// ------------------------------------------------------------------ merge: U + ordering
-// U(:, j) = normalised zhat_i / (d_i - lambda_j), stored at Ubuf[(s+i) + (s+j)*ld].
+// ------------------------------------------------------------------ merge: ordering
 // Final order = merge of the ascending roots with the ascending deflated values.
-__global__ void __launch_bounds__(128) umat_kernel(DcArgs a, int level, int nmat)
+__global__ void __launch_bounds__(128) order_kernel(DcArgs a, int level, int nmat)
 {
     const int nnode = 1 << level;
     const int mat = blockIdx.y / nnode, q = blockIdx.y % nnode;
@@ -499,35 +499,19 @@ __global__ void __launch_bounds__(128) umat_kernel(DcArgs a, int level, int nmat
     const int k = islot[a.oPerm + (size_t)IX_KP * ld + s];
     const int ndef = n - k;
     double *aux = slot + a.oAux;
-    const double *d = aux + (size_t)AX_DLAM * ld + s;
-    const double *mu = aux + (size_t)AX_MU * ld + s;
-    const double *zhat = aux + (size_t)AX_ZHAT * ld + s;
     const double *lamroot = aux + (size_t)AX_LAMROOT * ld + s;
     const double *defl = aux + (size_t)AX_DEFL * ld + s + k;
     double *lamnew = aux + (size_t)AX_LAMNEW * ld + s;
-    const int32_t *origin = islot + a.oPerm + (size_t)IX_ORIGIN * ld + s;
     int32_t *posroot = islot + a.oPerm + (size_t)IX_POSROOT * ld + s;
     int32_t *defpos = islot + a.oPerm + (size_t)IX_DEFPOS * ld + s;
-    double *U = slot + a.oU;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < k) {
-        const int j = t;
-        const double dorg = d[origin[j]], m = mu[j];
-        double *uc = U + (size_t)(s + j) * ld + s;
-        double nrm = 0.0;
-        for (int i = 0; i < k; ++i) {
-            const double val = zhat[i] / ((d[i] - dorg) - m);
-            uc[i] = val;
-            nrm += val * val;
-        }
-        const double inv = 1.0 / sqrt(nrm);
-        for (int i = 0; i < k; ++i) uc[i] *= inv;
         // position among deflated values: count deflated < root (ties: roots first)
-        const double x = lamroot[j];
+        const double x = lamroot[t];
         int lo = 0, hi = ndef;
         while (lo < hi) { const int m2 = (lo + hi) >> 1; if (defl[m2] < x) lo = m2 + 1; else hi = m2; }
-        posroot[j] = j + lo;
-        lamnew[j + lo] = x;
+        posroot[t] = t + lo;
+        lamnew[t + lo] = x;
     } else if (t < n) {
         const int jd = t - k;
         const double x = defl[jd];
@@ -536,6 +520,64 @@ __global__ void __launch_bounds__(128) umat_kernel(DcArgs a, int level, int nmat
         defpos[jd] = jd + lo;
         lamnew[jd + lo] = x;
     }
+}
+
+// k eigenvalues nearest sigma = a contiguous window of the ascending spectrum
+__global__ void window_kernel(int N, const double *base, size_t slot, size_t off, int k,
+                              double sigma, int32_t *sel0, int nmat)
+{
+    const int mat = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mat >= nmat) return;
+    const double *lam = base + (size_t)mat * slot + off;
+    int lo = 0, hi = N;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (lam[m] < sigma) lo = m + 1; else hi = m; }
+    int left = lo - 1, right = lo;
+    for (int t = 0; t < k; ++t) {
+        const bool canL = left >= 0, canR = right < N;
+        if (canL && (!canR || fabs(lam[left] - sigma) <= fabs(lam[right] - sigma))) --left;
+        else ++right;
+    }
+    sel0[mat] = left + 1;
+}
+
+// ------------------------------------------------------------------ merge: U
+// U(:, j) = normalised zhat_i / (d_i - lambda_j), stored at Ubuf[(s+i) + (s+j)*ld].
+// One warp per column (coalesced); at level 0 only the columns inside the requested
+// eigenvalue window are built.  grid = (ceil(nmax / 4), nmat * nnode), block = 128.
+__global__ void __launch_bounds__(128) umat_kernel(DcArgs a, int level, int nmat)
+{
+    const int nnode = 1 << level;
+    const int mat = blockIdx.y / nnode, q = blockIdx.y % nnode;
+    if (mat >= nmat) return;
+    double *slot = a.base + (size_t)mat * a.slot;
+    int32_t *islot = a.ibase + (size_t)mat * a.islot;
+    const int ld = a.Npad;
+    const int s = node_start(a.N, level, q);
+    const int k = islot[a.oPerm + (size_t)IX_KP * ld + s];
+    const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= k) return;
+    const int32_t *posroot = islot + a.oPerm + (size_t)IX_POSROOT * ld + s;
+    if (level == 0 && a.wink > 0) {
+        const int w0 = a.win0[mat], p = posroot[j];
+        if (p < w0 || p >= w0 + a.wink) return;
+    }
+    double *aux = slot + a.oAux;
+    const double *d = aux + (size_t)AX_DLAM * ld + s;
+    const double *mu = aux + (size_t)AX_MU * ld + s;
+    const double *zhat = aux + (size_t)AX_ZHAT * ld + s;
+    const int32_t *origin = islot + a.oPerm + (size_t)IX_ORIGIN * ld + s;
+    const double dorg = d[origin[j]], m = mu[j];
+    double *uc = slot + a.oU + (size_t)(s + j) * ld + s;
+    double nrm = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double val = zhat[i] / ((d[i] - dorg) - m);
+        uc[i] = val;
+        nrm += val * val;
+    }
+    nrm = warp_sum(nrm);
+    const double inv = 1.0 / sqrt(nrm);
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) uc[i] *= inv;
 }
 
 // ------------------------------------------------------------------ merge: finish
@@ -563,12 +605,24 @@ __global__ void __launch_bounds__(256) merge_finish_kernel(DcArgs a, int level, 
         P.A = Qold + s;                    // rows s..s+n
         P.lda = ld;
         P.aidx = islot + a.oPerm + (size_t)IX_COLSRC * ld + s;
-        P.B = slot + a.oU + (size_t)s * ld + s;
+        const int32_t *posroot = islot + a.oPerm + (size_t)IX_POSROOT * ld + s;
+        int jlo = 0, jn = k;
+        if (level == 0 && a.wink > 0) {
+            // roots keep their order, so the selected ones are a contiguous range
+            const int w0 = a.win0[mat], w1 = w0 + a.wink;
+            int lo = 0, hi = k;
+            while (lo < hi) { const int m2 = (lo + hi) >> 1; if (posroot[m2] < w0) lo = m2 + 1; else hi = m2; }
+            jlo = lo;
+            hi = k;
+            while (lo < hi) { const int m2 = (lo + hi) >> 1; if (posroot[m2] < w1) lo = m2 + 1; else hi = m2; }
+            jn = lo - jlo;
+        }
+        P.B = slot + a.oU + (size_t)(s + jlo) * ld + s;
         P.ldb = ld;
         P.C = Qnew + (size_t)s * ld + s;   // cmap holds positions local to the block
         P.ldc = ld;
-        P.cmap = islot + a.oPerm + (size_t)IX_POSROOT * ld + s;   // local positions
-        P.M = n; P.Ncols = k; P.K = k;
+        P.cmap = posroot + jlo;            // local positions
+        P.M = n; P.Ncols = jn; P.K = k;
         probs[blockIdx.x] = P;
     }
     for (int j = threadIdx.x; j < n; j += blockDim.x) lam[s + j] = lamnew[j];
@@ -593,6 +647,10 @@ __global__ void __launch_bounds__(256) copy_deflated_kernel(DcArgs a, int level,
     double *Qnew = slot + (cur ? a.oQa : a.oQb);
     const int src_col = islot[a.oPerm + (size_t)IX_DEFSRC * ld + s + k + jd];
     const int pos = islot[a.oPerm + (size_t)IX_DEFPOS * ld + s + jd];
+    if (level == 0 && a.wink > 0) {
+        const int w0 = a.win0[mat];
+        if (pos < w0 || pos >= w0 + a.wink) return;
+    }
     const double *src = Qold + (size_t)src_col * ld + s;
     double *dst = Qnew + (size_t)(s + pos) * ld + s;
     for (int r = lane; r < n; r += 32) dst[r] = src[r];
@@ -610,7 +668,8 @@ __global__ void zero_kernel(double *base, size_t slot, size_t off, size_t count,
 
 }  // namespace
 
-int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
+int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches, int sel_k,
+              double sigma, int32_t *d_sel0)
 {
     const EigLayout &L = S.L;
     static_assert(sizeof(GemmProblem) <= EIG_PROB_BYTES, "GemmProblem too large");
@@ -629,7 +688,9 @@ int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     a.oU = L.oU;
     a.oD = L.oD; a.oE = L.oE; a.oLam = L.oLam; a.oAux = L.oAux;
     a.oPerm = L.oPerm; a.oIdx = L.oIdx;
-    a.out_lo_dummy = 0;
+    const bool window = sel_k > 0 && sel_k < L.N && d_sel0 != nullptr;
+    a.win0 = d_sel0;
+    a.wink = window ? sel_k : 0;
     int nl = 0;
     const size_t nn = (size_t)L.Npad * L.Npad;
     zero_kernel<<<148 * 8, 256, 0, st>>>(S.dbl, L.slot_doubles, L.oQ1, nn, nmat);
@@ -649,13 +710,30 @@ int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
         const dim3 g1((nmax + 127) / 128, gy);
         secular_kernel<<<g1, 128, 0, st>>>(a, level, nmat);
         zhat_kernel<<<g1, 128, 0, st>>>(a, level, nmat);
-        umat_kernel<<<g1, 128, 0, st>>>(a, level, nmat);
+        order_kernel<<<g1, 128, 0, st>>>(a, level, nmat);
+        if (level == 0 && window) {
+            // final spectrum is known now: pick the k eigenvalues nearest sigma, then build
+            // only those eigenvectors (U columns, GEMM columns, deflated copies)
+            window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(
+                L.N, S.dbl, L.slot_doubles, L.oAux + (size_t)AX_LAMNEW * L.Npad, sel_k, sigma, d_sel0, nmat);
+            ++nl;
+        }
+        umat_kernel<<<dim3((nmax + 3) / 4, gy), 128, 0, st>>>(a, level, nmat);
         merge_finish_kernel<<<gy, 256, 0, st>>>(a, level, nmat, cur, probs);
         copy_deflated_kernel<<<dim3((nmax + 7) / 8, gy), 256, 0, st>>>(a, level, nmat, cur);
         const int tiles = (nmax + 63) / 64;
         grouped_dgemm_kernel<<<dim3(tiles * tiles, gy), 256, 0, st>>>(probs, tiles);
-        nl += 7;
+        nl += 8;
         cur ^= 1;
+    }
+    if (D == 0 && sel_k > 0 && d_sel0 != nullptr) {
+        window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(L.N, S.dbl, L.slot_doubles, L.oLam,
+                                                           sel_k < L.N ? sel_k : L.N, sigma, d_sel0, nmat);
+        ++nl;
+    } else if (!window && sel_k > 0 && d_sel0 != nullptr) {
+        window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(L.N, S.dbl, L.slot_doubles, L.oLam,
+                                                           L.N, sigma, d_sel0, nmat);
+        ++nl;
     }
     ARCB200_LAUNCH_CHECK("stedc kernels");
     if (launches) *launches += nl;

@@ -140,25 +140,6 @@ __global__ void store_dense_kernel(int N, int Npad, const double *base, size_t s
     }
 }
 
-// ---------------------------------------------------------------- selection
-// k eigenvalues nearest sigma form a contiguous window of the ascending spectrum.
-__global__ void select_window_kernel(int N, const double *base, size_t slot, size_t oLam, int k,
-                                     double sigma, int32_t *sel0, int nmat)
-{
-    const int mat = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mat >= nmat) return;
-    const double *lam = base + (size_t)mat * slot + oLam;
-    int lo = 0, hi = N;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (lam[m] < sigma) lo = m + 1; else hi = m; }
-    int left = lo - 1, right = lo;    // next candidates
-    for (int t = 0; t < k; ++t) {
-        const bool canL = left >= 0, canR = right < N;
-        if (canL && (!canR || fabs(lam[left] - sigma) <= fabs(lam[right] - sigma))) --left;
-        else ++right;
-    }
-    sel0[mat] = left + 1;
-}
-
 // ---------------------------------------------------------------- epilogue
 // one warp per eigenvector: eigenvalue, highlight, top-k composition
 constexpr int MAXTOP = 8;
@@ -239,15 +220,9 @@ int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma
     const int cluster = eig_pick_cluster(L.N, nmat);
     int rc = eig_sytrd(W.S, nmat, cluster, st, launches);
     if (rc) return rc;
-    rc = eig_stedc(W.S, nmat, st, launches);
+    rc = eig_stedc(W.S, nmat, st, launches, window ? nsel : 0, sigma, window ? W.sel0 : nullptr);
     if (rc) return rc;
-    const int32_t *sel = nullptr;
-    if (window) {
-        select_window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(
-            L.N, W.S.dbl, L.slot_doubles, L.oLam, nsel, sigma, W.sel0, nmat);
-        *launches += 1;
-        sel = W.sel0;
-    }
+    const int32_t *sel = window ? W.sel0 : nullptr;
     return eig_ormtr(W.S, nmat, sel, nsel, st, launches);
 }
 
