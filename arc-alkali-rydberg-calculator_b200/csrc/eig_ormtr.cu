@@ -232,6 +232,151 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_kernel(OrmArgs a)
     }
 }
 
+
+// Shared-memory resident variant: the whole slab Z[:, NT*8 columns] stays in shared memory
+// across all reflector blocks (read once, written once); only V streams from L2.
+// LDZ = Npad + 4 keeps the DMMA fragment accesses bank-conflict free.
+template <int NT>
+__global__ void __launch_bounds__(OT_THREADS) ormtr_smem_kernel(OrmArgs a)
+{
+    constexpr int SW = NT * 8;
+    const int slab = blockIdx.x, mat = blockIdx.y;
+    double *slot = a.base + (size_t)mat * a.slot;
+    const double *__restrict__ A = slot + a.oA;
+    const double *Tall = slot + a.oTfac;
+    const int N = a.N, lda = a.Npad, LDZ = a.Npad + 4;
+    const int col0 = (a.sel0 ? a.sel0[mat] : 0) + SW * slab;
+    const int ncol = min(SW, a.nsel - SW * slab);
+    double *Z = slot + a.oZ + (size_t)col0 * lda;
+    extern __shared__ double orm_smem[];
+    double *Zs = orm_smem;                                     // [SW][LDZ]
+    double(*Wred)[TS] = reinterpret_cast<double(*)[TS]>(orm_smem + (size_t)SW * LDZ);   // [SW][36]
+    double(*Tsm)[33] = reinterpret_cast<double(*)[33]>(orm_smem + (size_t)SW * LDZ + SW * TS);
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int grp = lane >> 2, tig = lane & 3;
+
+    for (int cc = wid; cc < SW; cc += OT_WARPS)
+        for (int r = lane; r < lda; r += 32)
+            Zs[(size_t)cc * LDZ + r] = (r < N && cc < ncol) ? Z[r + (size_t)cc * lda] : 0.0;
+    __syncthreads();
+
+    for (int b = a.NBR - 1; b >= 0; --b) {
+        const int c0 = 32 * b;
+        const int chunk0 = (c0 + 1) & ~31;
+        for (int t = tid; t < 1024; t += OT_THREADS) Tsm[t >> 5][t & 31] = Tall[(size_t)b * 1024 + t];
+        for (int t = tid; t < SW * TS; t += OT_THREADS) (&Wred[0][0])[t] = 0.0;
+        // ---------------- pass 1: W = V^T Z ----------------
+        double acc[4][NT][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int r0 = chunk0 + 32 * wid; r0 < N; r0 += 32 * OT_WARPS) {
+            double af[8][4];
+            const bool top = r0 < c0 + 64;      // rows that touch the unit / zero part of V
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 4 * ks + tig, c = c0 + 8 * i + grp;
+                    af[ks][i] = (top || r >= N || c > N - 2) ? vval(A, lda, N, r, c) : A[r + (size_t)c * lda];
+                }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double bf[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bf[j] = Zs[(size_t)(8 * j + grp) * LDZ + r0 + 4 * ks + tig];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma_o(acc[i][j][0], acc[i][j][1], af[ks][i], bf[j]);
+            }
+        }
+        __syncthreads();
+        for (int w = 0; w < OT_WARPS; ++w) {
+            if (wid == w) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) Wred[8 * j + 2 * tig + h][8 * i + grp] += acc[i][j][h];
+            }
+            __syncthreads();
+        }
+        // W <- T W
+        double wn[(SW * 32 + OT_THREADS - 1) / OT_THREADS];
+#pragma unroll
+        for (int p = 0; p < (SW * 32 + OT_THREADS - 1) / OT_THREADS; ++p) {
+            const int t = tid + p * OT_THREADS;
+            double sacc = 0.0;
+            if (t < SW * 32) {
+                const int n = t >> 5, jr = t & 31;
+                for (int l = jr; l < 32; ++l) sacc += Tsm[jr][l] * Wred[n][l];
+            }
+            wn[p] = sacc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < (SW * 32 + OT_THREADS - 1) / OT_THREADS; ++p) {
+            const int t = tid + p * OT_THREADS;
+            if (t < SW * 32) Wred[t >> 5][t & 31] = wn[p];
+        }
+        __syncthreads();
+        // ---------------- pass 2: Z -= V W ----------------
+        for (int r0 = chunk0 + 32 * wid; r0 < N; r0 += 32 * OT_WARPS) {
+            const bool top = r0 < c0 + 64;
+            double af[8][4];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 8 * i + grp, c = c0 + 4 * ks + tig;
+                    af[ks][i] = -((top || r >= N || c > N - 2) ? vval(A, lda, N, r, c) : A[r + (size_t)c * lda]);
+                }
+            double c2[4][NT][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        c2[i][j][h] = Zs[(size_t)(8 * j + 2 * tig + h) * LDZ + r0 + 8 * i + grp];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double bf[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bf[j] = Wred[8 * j + grp][4 * ks + tig];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma_o(c2[i][j][0], c2[i][j][1], af[ks][i], bf[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        Zs[(size_t)(8 * j + 2 * tig + h) * LDZ + r0 + 8 * i + grp] = c2[i][j][h];
+        }
+        __syncthreads();
+    }
+    for (int cc = wid; cc < ncol; cc += OT_WARPS)
+        for (int r = lane; r < N; r += 32) Z[r + (size_t)cc * lda] = Zs[(size_t)cc * LDZ + r];
+}
+
+template <int NT>
+int launch_ormtr_smem(const OrmArgs &a, int nmat, cudaStream_t st)
+{
+    const int SW = NT * 8;
+    const size_t smem = ((size_t)SW * (a.Npad + 4) + (size_t)SW * TS + 32 * 33) * sizeof(double);
+    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_smem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nslab = (a.nsel + SW - 1) / SW;
+    ormtr_smem_kernel<NT><<<dim3(nslab, nmat), OT_THREADS, smem, st>>>(a);
+    return 0;
+}
+
 }  // namespace
 
 int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
@@ -246,6 +391,21 @@ int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cuda
     a.oA = L.oA; a.oTau = L.oTau; a.oTfac = L.oTfac; a.oZ = L.oQ1;
     a.nsel = nsel; a.sel0 = d_sel0;
     larft_kernel<<<dim3(a.NBR, nmat), OT_THREADS, 0, st>>>(a);
+    // shared-memory resident slab when it fits (<= 200 KiB): widest slab first
+    const size_t budget = 200 * 1024;
+    auto fits = [&](int sw) {
+        return ((size_t)sw * (L.Npad + 4) + (size_t)sw * TS + 32 * 33) * sizeof(double) <= budget;
+    };
+    int rcs = -100;
+    if (fits(32)) rcs = launch_ormtr_smem<4>(a, nmat, st);
+    else if (fits(16)) rcs = launch_ormtr_smem<2>(a, nmat, st);
+    else if (fits(8)) rcs = launch_ormtr_smem<1>(a, nmat, st);
+    if (rcs != -100) {
+        if (rcs) return rcs;
+        ARCB200_LAUNCH_CHECK("ormtr_smem kernel");
+        if (launches) *launches += 2;
+        return 0;
+    }
     const int nslab = (nsel + 31) / 32;
     const size_t smem = (size_t)(2 * OT_WARPS * 32 * TS + 32 * TS + 32 * 33) * sizeof(double);
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
