@@ -56,14 +56,17 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
 // coalesced 256-byte warp request and all of them are in flight together.
 __device__ __forceinline__ double panel_row_dot(const double *__restrict__ vcol,
                                                 const double *__restrict__ wcol, int ld,
-                                                const double *a, const double *b)
+                                                const double *a, const double *b, int ncols)
 {
-    double x[32], y[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { x[j] = vcol[(size_t)j * ld]; y[j] = wcol[(size_t)j * ld]; }
+    // only the first `ncols` panel columns are populated (warp-uniform): 8 at a time
     double s0 = 0.0, s1 = 0.0;
+    for (int j0 = 0; j0 < ncols; j0 += 8) {
+        double x[8], y[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { s0 += x[j] * a[j]; s1 += y[j] * b[j]; }
+        for (int j = 0; j < 8; ++j) { x[j] = vcol[(size_t)(j0 + j) * ld]; y[j] = wcol[(size_t)(j0 + j) * ld]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0 += x[j] * a[j0 + j]; s1 += y[j] * b[j0 + j]; }
+    }
     return s0 + s1;
 }
 
@@ -73,8 +76,11 @@ __device__ __forceinline__ void group_sync(cg::cluster_group &cl)
     if (CL) cl.sync(); else __syncthreads();
 }
 
-template <bool CL>
-__global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
+// LEAN: no register double-buffering of the symv tiles -> <= 128 registers, two CTAs per SM.
+// Small matrices (few tiles per warp and column) are bound by the per-column latency chain,
+// so a second resident matrix per SM hides more than tile prefetching does.
+template <bool CL, bool LEAN>
+__global__ void __launch_bounds__(SY_THREADS, LEAN ? 2 : 1) sytrd_kernel(SytrdArgs a)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = CL ? (int)cluster.num_blocks() : 1;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 wtr[r] = 0.0;
                 if (r >= c && r < N) {
                     double av = __ldcg(&A[r + (size_t)c * lda]);
-                    av -= panel_row_dot(Vp + r, Wp + r, lda, pw, pv);
+                    av -= panel_row_dot(Vp + r, Wp + r, lda, pw, pv, i);
                     A[r + (size_t)c * lda] = av;
                     if (r >= c + 2) nrm += av * av;
                     if (r == c) dd[c] = av;
@@ -290,8 +296,17 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 auto advance = [&](int &I_, int &J_) {
                     if (++I_ >= NB) { ++J_; I_ = J_; }
                 };
-                if (ntile > 0) load_tile(ta, I, J);
-                while (ntile > 0) {
+                if (LEAN) {
+                    while (ntile > 0) {
+                        int nI = I, nJ = J;
+                        advance(nI, nJ);
+                        load_tile(ta, I, J);
+                        consume(ta, I, J, ntile == 1 || nJ != J);
+                        I = nI; J = nJ; --ntile;
+                    }
+                }
+                if (!LEAN && ntile > 0) load_tile(ta, I, J);
+                while (!LEAN && ntile > 0) {
                     int nI = I, nJ = J;
                     advance(nI, nJ);
                     if (ntile > 1) load_tile(tb, nI, nJ);
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
                 const int r = 32 * I + lane;
                 if (r >= c + 1 && r < N) {
                     double w = __ldcg(&wtr[r]);
-                    w -= panel_row_dot(Vp + r, Wp + r, lda, t1s, t2s);
+                    w -= panel_row_dot(Vp + r, Wp + r, lda, t1s, t2s, i);
                     w *= tau;
                     pacc += w * v[r];
                     Wp[(size_t)i * lda + r] = w;
@@ -444,8 +459,8 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_kernel(SytrdArgs a)
     }  // panels
 #ifdef SYTRD_PROFILE
     if (mat == 0 && tid == 0) {
-        printf("sytrd prof rank %d: col-setup %lld ph1 %lld B1 %lld vload %lld dots %lld symv %lld B2wait %lld ph3 %lld B3wait %lld ph4 %lld update %lld (Mcycles)\n", rank,
-               prof_t[0] / 1000000, prof_t[1] / 1000000, prof_t[2] / 1000000, prof_t[3] / 1000000, prof_t[4] / 1000000, prof_t[5] / 1000000, prof_t[6] / 1000000, prof_t[7] / 1000000, prof_t[8] / 1000000, prof_t[9] / 1000000, prof_t[10] / 1000000);
+        printf("sytrd prof rank %d: col-setup %lld ph1 %lld B1 %lld vload %lld dots %lld symv %lld B2wait %lld ph3 %lld B3wait %lld ph4 %lld update %lld (units of 10 kcycles)\n", rank,
+               prof_t[0] / 10000, prof_t[1] / 10000, prof_t[2] / 10000, prof_t[3] / 10000, prof_t[4] / 10000, prof_t[5] / 10000, prof_t[6] / 10000, prof_t[7] / 10000, prof_t[8] / 10000, prof_t[9] / 10000, prof_t[10] / 10000);
     }
 #endif
 }
@@ -476,14 +491,20 @@ int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *la
         return -1;
     }
     if (cluster <= 1) {
-        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sytrd_kernel<false><<<nmat, SY_THREADS, smem, st>>>(a);
+        if (L.N <= 512 && nmat > 148) {
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<false, true>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sytrd_kernel<false, true><<<nmat, SY_THREADS, smem, st>>>(a);
+        } else {
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<false, false>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sytrd_kernel<false, false><<<nmat, SY_THREADS, smem, st>>>(a);
+        }
     } else {
-        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true>,
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true, false>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (cluster > 8)
-            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true>,
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<true, false>,
                                                     cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nmat * cluster);
@@ -497,7 +518,7 @@ int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *la
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        ARCB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sytrd_kernel<true>, a));
+        ARCB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sytrd_kernel<true, false>, a));
     }
     ARCB200_LAUNCH_CHECK("sytrd_kernel");
     if (launches) *launches += 1;
