@@ -144,21 +144,75 @@ __global__ void __launch_bounds__(SY_THREADS, LEAN ? 2 : 1) sytrd_kernel(SytrdAr
 
             PROF(0)
             // ---------------- phase 1: lazy update of column c --------------------
-            double nrm = 0.0;
+            double nrm = 0.0, u1acc = 0.0, u2acc = 0.0;
             for (int I = first_owned(c / 32); I < NB; I += nW) {
                 const int r = 32 * I + lane;
                 wtr[r] = 0.0;
-                if (r >= c && r < N) {
-                    double av = __ldcg(&A[r + (size_t)c * lda]);
-                    av -= panel_row_dot(Vp + r, Wp + r, lda, pw, pv, i);
+                const bool live = (r >= c && r < N);
+                // panel row (V(r, 0..i), W(r, 0..i)): loaded ONCE, used for the lazy column
+                // update and for the panel dot products W^T a, V^T a of the new reflector
+                double x[32], y[32];
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                    if (j0 < i) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            x[j0 + j] = Vp[(size_t)(j0 + j) * lda + r];
+                            y[j0 + j] = Wp[(size_t)(j0 + j) * lda + r];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j0 + j] = y[j0 + j] = 0.0;
+                    }
+                }
+                double av = 0.0;
+                if (live) {
+                    av = __ldcg(&A[r + (size_t)c * lda]);
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { s0 += x[j] * pw[j]; s1 += y[j] * pv[j]; }
+                    av -= s0 + s1;
                     A[r + (size_t)c * lda] = av;
                     if (r >= c + 2) nrm += av * av;
                     if (r == c) dd[c] = av;
                     if (r == c + 1) scr[0] = av;
                 }
+                if (i > 0) {
+                    const double ar = (live && r >= c + 1) ? av : 0.0;     // row c is the diagonal
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = y[j] * ar;
+                    __syncwarp();
+                    {
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
+                        u1acc += s0 + s1;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = x[j] * ar;
+                    __syncwarp();
+                    {
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
+                        u2acc += s0 + s1;
+                    }
+                    __syncwarp();
+                }
             }
             if (c == N - 1) break;
             nrm = warp_sum(nrm);
+            sred[wid][lane] = u1acc;
+            sred[wid][32 + lane] = u2acc;
+            __syncthreads();
+            if (wid == 0) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < SY_WARPS; ++q) { s1 += sred[q][lane]; s2 += sred[q][32 + lane]; }
+                __stcg(&scr[64 + 64 * rank + lane], s1);
+                __stcg(&scr[64 + 64 * rank + 32 + lane], s2);
+            }
+            __syncthreads();
             if (lane == 0) sred[wid][0] = nrm;
             __syncthreads();
             if (tid == 0) {
@@ -193,7 +247,23 @@ __global__ void __launch_bounds__(SY_THREADS, LEAN ? 2 : 1) sytrd_kernel(SytrdAr
                 continue;
             }
 
-            // ---------------- phase 2: v, symmetric mat-vec, panel dots ------------
+            // panel dot products of the scaled reflector:  t = scale * (P^T a) + (1 - scale*alpha) * P(c+1, :)
+            if (wid == 0) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < C; ++q) {
+                    s1 += __ldcg(&scr[64 + 64 * q + lane]);
+                    s2 += __ldcg(&scr[64 + 64 * q + 32 + lane]);
+                }
+                double t1 = 0.0, t2 = 0.0;
+                if (lane < i) {
+                    const double corr = 1.0 - scale * alpha;
+                    t1 = scale * s1 + corr * __ldcg(&Wp[(size_t)lane * lda + c + 1]);
+                    t2 = scale * s2 + corr * __ldcg(&Vp[(size_t)lane * lda + c + 1]);
+                }
+                t1s[lane] = t1;
+                t2s[lane] = t2;
+            }
+            // ---------------- phase 2: v, symmetric mat-vec ------------------------
             for (int r = tid; r < lda; r += SY_THREADS) {
                 double x = 0.0;
                 if (r == c + 1) x = 1.0;
@@ -204,42 +274,11 @@ __global__ void __launch_bounds__(SY_THREADS, LEAN ? 2 : 1) sytrd_kernel(SytrdAr
 
             PROF(3)
             const int Jmin = (c + 1) / 32;
-            double t1acc = 0.0, t2acc = 0.0;
-            // V panel column + panel dot products W^T v, V^T v for the block rows this warp
-            // owns: coalesced loads (lane <-> row), products transposed through shared memory
-            // so that lane j ends up with the sum over the 32 rows (like the symv tiles)
+            // V panel column of the new reflector (rows this warp owns)
             for (int I = first_owned(Jmin); I < NB; I += nW) {
                 const int r = 32 * I + lane;
-                const double vr_ = v[r];
-                if (r >= c + 1) Vp[(size_t)i * lda + r] = vr_;
-                if (i == 0) continue;
-                double x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = Wp[(size_t)j * lda + r];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = x[j] * vr_;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = Vp[(size_t)j * lda + r];
-                {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
-                    t1acc += s0 + s1;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mytile[j * TPAD + lane] = x[j] * vr_;
-                __syncwarp();
-                {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 32; q += 2) { s0 += mytile[lane * TPAD + q]; s1 += mytile[lane * TPAD + q + 1]; }
-                    t2acc += s0 + s1;
-                }
-                __syncwarp();
+                if (r >= c + 1) Vp[(size_t)i * lda + r] = v[r];
             }
-            if (lane >= i) { t1acc = 0.0; t2acc = 0.0; }
             PROF(4)
             {
                 // symmetric mat-vec over the lower-triangular tiles (I >= J >= Jmin), dealt to
@@ -320,29 +359,10 @@ __global__ void __launch_bounds__(SY_THREADS, LEAN ? 2 : 1) sytrd_kernel(SytrdAr
                 }
             }
             PROF(5)
-            sred[wid][lane] = t1acc;
-            sred[wid][32 + lane] = t2acc;
-            __syncthreads();
-            if (wid == 0) {
-                double s1 = 0.0, s2 = 0.0;
-                for (int q = 0; q < SY_WARPS; ++q) { s1 += sred[q][lane]; s2 += sred[q][32 + lane]; }
-                __stcg(&scr[64 + 64 * rank + lane], s1);
-                __stcg(&scr[64 + 64 * rank + 32 + lane], s2);
-            }
             group_sync<CL>(cluster);                                   // ---- B2
             PROF(6)
 
             // ---------------- phase 3 --------------------------------------------
-            if (wid == 0) {
-                double s1 = 0.0, s2 = 0.0;
-                for (int q = 0; q < C; ++q) {
-                    s1 += __ldcg(&scr[64 + 64 * q + lane]);
-                    s2 += __ldcg(&scr[64 + 64 * q + 32 + lane]);
-                }
-                t1s[lane] = s1;
-                t2s[lane] = s2;
-            }
-            __syncthreads();
             double pacc = 0.0;
             for (int I = first_owned(Jmin); I < NB; I += nW) {
                 const int r = 32 * I + lane;
