@@ -23,6 +23,9 @@ STATE_DTYPE = np.dtype([
     ("a4", "f8"), ("rc", "f8"), ("mu", "f8"), ("l", "i4"), ("Z", "i4"),
     ("length", "i4"), ("_pad", "i4")], align=True)
 assert STATE_DTYPE.itemsize == 144
+GRAM_DTYPE = np.dtype([("row0", "i4"), ("nrows", "i4"), ("col0", "i4"), ("ncols", "i4"),
+                       ("power", "i4"), ("kmax", "i4"), ("out_off", "i8")], align=True)
+assert GRAM_DTYPE.itemsize == 32
 
 _SIGNATURES = {
     "arcb200_abi_version": (c_int, []),
@@ -33,6 +36,8 @@ _SIGNATURES = {
                                       c_vp, c_vp, c_i32]),
     "arcb200_radial_integrals": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_vp]),
+    "arcb200_radial_gram": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    c_i32, c_vp, c_vp, c_i32, c_i32, c_i32]),
     "arcb200_semiclassical_table": (c_int, [c_int, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,
                                             c_vp]),
     "arcb200_sweep_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),

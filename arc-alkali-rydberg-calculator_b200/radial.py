@@ -90,6 +90,97 @@ class RadialBatch:
     def integrals(self, pairs):
         return self.integrals_device(pairs).cpu().numpy()
 
+    def gram_device(self, blocks):
+        """blocks: list of (row_states, col_states, power).  Returns (out tensor, offsets):
+        block g's dense |rows| x |cols| table starts at offsets[g] (row-major).  Tensor-core
+        path (arcb200_radial_gram): every wavefunction is read once per block pair."""
+        import torch
+        lib = _lib.load()
+        dev = torch.device("cuda", self.device)
+        rows, cols, desc, off = [], [], np.zeros(len(blocks), dtype=_lib.GRAM_DTYPE), 0
+        offs = []
+        for g, (ra, cb, power) in enumerate(blocks):
+            ra = np.asarray(ra, dtype=np.int32)
+            cb = np.asarray(cb, dtype=np.int32)
+            desc[g] = (len(rows), len(ra), len(cols), len(cb), int(power),
+                       int(min(self.lengths[ra].max(), self.lengths[cb].max())), off)
+            offs.append(off)
+            rows.extend(ra.tolist())
+            cols.extend(cb.tolist())
+            off += len(ra) * len(cb)
+        out = torch.zeros(max(off, 1), dtype=torch.float64, device=dev)
+        if not blocks:
+            return out, offs
+        imax = int(np.argmax(self.lengths))
+        Lg = int(self.lengths[imax])
+        d_rgrid = self.d_r[int(self.offsets[imax]):]
+        d_wgt = torch.empty(2 * Lg, dtype=torch.float64, device=dev)
+        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(dev)
+        d_rows = torch.tensor(rows, dtype=torch.int32, device=dev)
+        d_cols = torch.tensor(cols, dtype=torch.int32, device=dev)
+        rc = lib.arcb200_radial_gram(
+            self.device, _lib.stream_ptr(self.device), len(blocks), _lib.ptr(d_desc),
+            _lib.ptr(d_rows), _lib.ptr(d_cols), _lib.ptr(self.d_states), _lib.ptr(self.d_offsets),
+            _lib.ptr(self.d_psi), _lib.ptr(d_rgrid), Lg, _lib.ptr(d_wgt), _lib.ptr(out),
+            int(desc["nrows"].max()), int(desc["ncols"].max()), int(desc["kmax"].max()))
+        _lib.check(rc, "arcb200_radial_gram")
+        self.kernel_launches += 3
+        return out, offs
+
+
+    def moments_device(self):
+        """<r>, <r^2> of every state (trapezoid(psi^2 r^p, r)), CUDA tensor [n, 2]."""
+        import torch
+        if getattr(self, "_moments", None) is None:
+            idx = np.arange(self.n, dtype=np.int32)
+            pr = np.concatenate([np.stack([idx, idx, np.full_like(idx, 1)], 1),
+                                 np.stack([idx, idx, np.full_like(idx, 2)], 1)])
+            self._moments = self.integrals_device(pr).reshape(2, self.n).t().contiguous()
+        return self._moments
+
+    def gram_refined_device(self, blocks, thresh=1e-5):
+        """Gram tables with per-element accuracy control.  The tensor-core sums carry an
+        absolute rounding error of ~2e-14 * int|psi_a psi_b| r^p; for strongly cancelling
+        elements (|value| < thresh * sqrt(<r^p>_a <r^p>_b), physically ~zero couplings) that
+        is no longer 1e-8 relative, so exactly those elements are recomputed by the
+        one-warp-per-pair kernel, whose summation order matches the reference's pairwise
+        trapezoid sum.  Returns (out, offsets, number of refined elements)."""
+        import torch
+        out, offs = self.gram_device(blocks)
+        if not blocks:
+            return out, offs, 0
+        dev = out.device
+        mom = self.moments_device()
+        rows_f, cols_f, pow_f = [], [], []
+        for ra, cb, power in blocks:
+            ra_t = torch.as_tensor(np.asarray(ra, dtype=np.int64), device=dev)
+            cb_t = torch.as_tensor(np.asarray(cb, dtype=np.int64), device=dev)
+            rows_f.append(ra_t.repeat_interleave(len(cb)))
+            cols_f.append(cb_t.repeat(len(ra)))
+            pow_f.append(torch.full((len(ra) * len(cb),), int(power), dtype=torch.int64, device=dev))
+        rows_f, cols_f, pow_f = torch.cat(rows_f), torch.cat(cols_f), torch.cat(pow_f)
+        n_el = rows_f.numel()
+        scale = torch.sqrt(mom[rows_f, pow_f - 1].abs() * mom[cols_f, pow_f - 1].abs())
+        flag = torch.nonzero(out[:n_el].abs() < thresh * scale).flatten()
+        if flag.numel():
+            # the per-pair kernel uses the r grid of its first state: put the lower-energy
+            # (= smaller stateEnergy) state first like the reference does
+            E = torch.as_tensor(self.states["stateEnergy"].copy(), device=dev)
+            a, b = rows_f[flag], cols_f[flag]
+            swap = E[a] > E[b]
+            lo, hi = torch.where(swap, b, a), torch.where(swap, a, b)
+            pairs = torch.stack([lo, hi, pow_f[flag]], 1).to(torch.int32).contiguous()
+            lib = _lib.load()
+            vals = torch.empty(flag.numel(), dtype=torch.float64, device=dev)
+            rc = lib.arcb200_radial_integrals(
+                self.device, _lib.stream_ptr(self.device), flag.numel(), _lib.ptr(pairs),
+                _lib.ptr(self.d_states), _lib.ptr(self.d_offsets), _lib.ptr(self.d_psi),
+                _lib.ptr(self.d_r), _lib.ptr(vals))
+            _lib.check(rc, "arcb200_radial_integrals")
+            self.kernel_launches += 1
+            out[flag] = vals
+        return out, offs, int(flag.numel())
+
 
 _GL_CACHE = {}
 

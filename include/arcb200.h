@@ -82,6 +82,27 @@ int arcb200_radial_integrals(int device, void *stream, int64_t npairs,
                              const int64_t *d_offsets, const double *d_psi,
                              const double *d_r, double *d_out);
 
+/* The same integrals for whole BLOCKS of state pairs as tensor-core Gram matrices:
+ * block g computes out[out_off + a*ncols + b] for a in rows[row0..row0+nrows),
+ * b in cols[col0..col0+ncols) (state indices), power 1|2.  All states must share the x grid
+ * origin and step (same atom, same innerLimit); d_rgrid[0..Lgrid) is the r grid of the LONGEST
+ * state of the batch, d_wgt a scratch of 2*Lgrid doubles, d_out must be zero-initialised.
+ * arcb200_gram_block_t = {int32 row0, nrows, col0, ncols, power, kmax; int64 out_off} (32 bytes),
+ * kmax = min(max La, max Lb).  Replaces the per-element loop over
+ * getRadialMatrixElement / getQuadrupoleMatrixElement in StarkMap.defineBasis
+ * (calculations_atom_single.py:816-833) and __makeRawMatrix2
+ * (calculations_atom_pairstate.py:939-1013). */
+typedef struct arcb200_gram_block {
+    int32_t row0, nrows, col0, ncols, power, kmax;
+    int64_t out_off;
+} arcb200_gram_block_t;
+int arcb200_radial_gram(int device, void *stream, int32_t nblocks, const void *d_blocks,
+                        const int32_t *d_rows, const int32_t *d_cols,
+                        const arcb200_state_t *d_states, const int64_t *d_offsets,
+                        const double *d_psi, const double *d_rgrid, int32_t Lgrid,
+                        double *d_wgt, double *d_out, int32_t max_rows, int32_t max_cols,
+                        int32_t max_k);
+
 /* Semiclassical radial elements used by all divalent atoms
  * (alkali_atom_functions.py:2683-2735 dipole, 2737-2802 quadrupole; the Anger
  * functions J_{dnu-+1}(-dnu) replace mpmath.angerj).  One warp per element.

@@ -121,3 +121,40 @@ def test_empty_and_tiny_batches():
     rb = radial.RadialBatch(recs)
     out = rb.integrals(np.zeros((0, 3), dtype=np.int32))
     assert out.shape == (0,)
+
+
+def test_gram_path_matches_per_pair_kernel(gold_dir):
+    """Tensor-core Gram path (opt-in, atom.fast_radial=True): golden elements to 1e-8, and
+    against the exact per-pair kernel to 1e-8 relative OR 3e-12 of the Cauchy-Schwarz scale
+    sqrt(<r^p>_a <r^p>_b) for strongly cancelling elements (documented in atoms.py)."""
+    import arc_b200
+    from arc_b200 import radial
+    g = json.load(open(os.path.join(gold_dir, "radial_golden.json")))["atoms"]["Rubidium"]
+    atom = arc_b200.Rubidium()
+    atom.fast_radial = True
+    atom.precompute_radial(dipole_pairs=[tuple(r[:6]) for r in g["dipole"]],
+                           quadrupole_pairs=[tuple(r[:6]) for r in g["quadrupole"]])
+    for r in g["dipole"]:
+        assert abs(atom.getRadialMatrixElement(*r[:6]) - r[6]) <= REL_ME * abs(r[6])
+    for r in g["quadrupole"]:
+        assert abs(atom.getQuadrupoleMatrixElement(*r[:6]) - r[6]) <= REL_ME * abs(r[6])
+    # dense block cross-check
+    sts = [(n, l, l + .5) for l in (0, 1, 2, 9) for n in range(25, 60, 3)]
+    recs = np.array([atom._state_record(*s) for s in sts])
+    rb = radial.RadialBatch(recs)
+    byl = {l: [i for i, s in enumerate(sts) if s[1] == l] for l in (0, 1, 2, 9)}
+    blocks = [(byl[0], byl[1], 1), (byl[1], byl[2], 1), (byl[0], byl[2], 2), (byl[9], byl[9], 2)]
+    out, offs, nref = rb.gram_refined_device(blocks, thresh=1e-4)
+    out = out.cpu().numpy()
+    mom = rb.moments_device().cpu().numpy()
+    E = recs["stateEnergy"]
+    for gi, (A, B, p) in enumerate(blocks):
+        pr = []
+        for a in A:
+            for b in B:
+                lo, hi = (a, b) if E[a] <= E[b] else (b, a)
+                pr.append((lo, hi, p))
+        ref = rb.integrals(np.array(pr, dtype=np.int32))
+        got = out[offs[gi]:offs[gi] + len(pr)]
+        scale = np.sqrt(np.abs(np.outer(mom[A, p - 1], mom[B, p - 1]))).ravel()
+        assert np.all(np.abs(got - ref) <= 1e-8 * np.abs(ref) + 3e-12 * scale)
