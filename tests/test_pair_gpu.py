@@ -77,3 +77,19 @@ def test_pair_c3(gold_dir):
     d = calc.matDiagonal.diagonal()
     assert np.abs(d - g["matDiagonal"]).max() <= 1e-9 * np.abs(d).max()
     _check(calc, g)
+
+
+def test_pair_c5_class_large_basis():
+    """BASELINE.json configs[4]: Rb 80D5/2+80D5/2, theta=pi/4, phi=0, Bz=1e-4 ->
+    272 channels, N=10384.  One R point, k=250, against LAPACK on the host."""
+    import arc_b200
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 80, 2, 2.5, 80, 2, 2.5, 2.5, 2.5)
+    calc.defineBasis(np.pi / 4, 0, 3, 4, 10e9, Bz=1e-4)
+    assert len(calc.channel) == 272 and len(calc.basisStates) == 10384
+    calc.diagonalise(np.array([3.0]), 250)
+    H = calc.matDiagonal.toarray() + calc.matR[0].toarray() / (3.0e-6) ** 3
+    assert np.abs(H - H.T).max() == 0.0
+    w = np.linalg.eigvalsh(H)
+    sel = np.sort(np.argsort(np.abs(w), kind="stable")[:250])
+    assert np.abs(calc.y[0] - w[sel]).max() <= 1e-9 * np.abs(w).max()
+    assert abs(np.sum(calc.highlight[0]) - 1.0) < 0.5      # a fraction of the pair state is in the window

@@ -129,3 +129,46 @@ def test_stark_c4_divalent_triplet_runs_and_matches_numpy():
     for f in range(len(F)):
         cid = np.concatenate([[0], np.cumsum(np.diff(y_o[f]) > 1e-7 * np.abs(y_o).max())])
         assert np.abs(np.bincount(cid, weights=hl[f]) - np.bincount(cid, weights=hl_o[f])).max() <= 1e-6
+
+
+def test_stark_driving_from_state_matches_reference(gold_dir):
+    """drivingFromState highlight (calculations_atom_single.py:887-962, 1003-1021)."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "stark_driving_golden.npz"))
+    a = g["args"]
+    calc = arc_b200.StarkMap(arc_b200.Rubidium())
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]))
+    d = g["drive"]
+    calc.diagonalise(g["fields"], drivingFromState=[int(d[0]), int(d[1]), float(d[2]), float(d[3]), int(d[4])])
+    assert abs(calc.maxCoupling - float(g["maxCoupling"])) <= 1e-8 * float(g["maxCoupling"])
+    y = np.array(calc.y)
+    scale = np.abs(g["y"]).max()
+    assert np.abs(y - g["y"]).max() <= 1e-9 * scale
+    hl = np.array(calc.highlight)
+    for f in range(len(g["fields"])):
+        cid = np.concatenate([[0], np.cumsum(np.diff(g["y"][f]) > 1e-7 * scale)])
+        assert np.abs(np.bincount(cid, weights=hl[f]) - np.bincount(cid, weights=g["highlight"][f])).max() <= 1e-6
+
+
+def test_pair_driving_from_state_and_k_clamp(gold_dir):
+    """drivingFromState for pair states (calculations_atom_pairstate.py:3332-3413) and the
+    noOfEigenvectors >= N-1 clamp (:3319-3327)."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "pair_driving_golden.npz"))
+    c, b, d = g["ctor"], g["basis"], g["drive"]
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]))
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]))
+    assert len(calc.basisStates) == int(g["N"])
+    calc.diagonalise(g["r"], int(g["k"]), drivingFromState=[int(d[0]), int(d[1]), float(d[2]), float(d[3]), int(d[4])])
+    assert calc.maxCoupledStateIndex == int(g["maxCoupledStateIndex"])
+    assert abs(calc.maxCoupling - float(g["maxCoupling"])) <= 1e-8 * float(g["maxCoupling"])
+    y = np.array(calc.y)
+    assert y.shape == g["y"].shape                      # clamped to N-1 eigenpairs
+    scale = max(np.abs(g["y"]).max(), 1e-3)
+    assert np.abs(y - g["y"]).max() <= 1e-7 * scale      # eigsh tol = 1e-6
+    hl = np.array(calc.highlight)
+    for i in range(len(g["r"])):
+        cid = np.concatenate([[0], np.cumsum(np.diff(g["y"][i]) > 1e-6 * scale)])
+        a_ = np.bincount(cid, weights=hl[i]); b_ = np.bincount(cid, weights=g["highlight"][i])
+        assert np.abs(a_[1:-1] - b_[1:-1]).max() <= 1e-6 if len(a_) > 2 else True

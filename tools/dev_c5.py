@@ -1,0 +1,26 @@
+"""BASELINE configs[4]-class run: Rb 80D5/2+80D5/2, theta=pi/4, Bz=1e-4, N ~ 10k; a few R points."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import arc_b200
+nR = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 250
+t0 = time.time()
+calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 80, 2, 2.5, 80, 2, 2.5, 2.5, 2.5)
+calc.defineBasis(np.pi / 4, 0, 3, 4, 10e9, Bz=1e-4)
+N = len(calc.basisStates)
+print("C5 defineBasis: %d channels, N=%d, matR nnz %d, %.1f s" % (len(calc.channel), N, calc.matR[0].nnz, time.time() - t0), flush=True)
+R = np.linspace(2, 20, nR)
+t0 = time.time()
+calc.diagonalise(R, k)
+torch.cuda.synchronize()
+dt = time.time() - t0
+print("diagonalise %d R points k=%d: %.2f s (%.2f s/point)" % (nR, k, dt, dt / nR), flush=True)
+# check one point against numpy on the host (dense eigh of the same matrix)
+i = 0
+H = calc.matDiagonal.toarray() + calc.matR[0].toarray() / (calc.r[i] * 1e-6) ** 3
+t0 = time.time()
+w = np.linalg.eigvalsh(H)
+print("numpy eigvalsh on host: %.1f s" % (time.time() - t0))
+sel = np.sort(np.argsort(np.abs(w), kind="stable")[:k])
+print("max |y - numpy| / scale = %.2e" % (np.abs(calc.y[i] - w[sel]).max() / np.abs(w).max()))

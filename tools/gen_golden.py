@@ -337,6 +337,33 @@ def gen_divalent(arc):
                 "stark_sr88_singlet_golden.npz", kwargs={"s": 0})
 
 
+def gen_driving(arc):
+    """drivingFromState variants: highlight = laser-coupling weighted admixture
+    (calculations_atom_single.py:887-962,1003-1021; calculations_atom_pairstate.py:3332-3413,3507-3520)."""
+    a = arc.Rubidium()
+    c = arc.StarkMap(a)
+    c.defineBasis(30, 2, 2.5, 0.5, 28, 32, 6)
+    F = np.linspace(0, 800, 4)
+    drive = [5, 1, 1.5, 0.5, 0]
+    c.diagonalise(F, drivingFromState=drive)
+    np.savez_compressed(os.path.join(GOLD, "stark_driving_golden.npz"),
+                        args=np.array([30, 2, 2.5, 0.5, 28, 32, 6], dtype=float), drive=np.array(drive, dtype=float),
+                        fields=F, y=np.array(c.y), highlight=np.array(c.highlight), maxCoupling=c.maxCoupling)
+    print("stark driving golden: N", len(c.basisStates), "maxCoupling", c.maxCoupling)
+    p = arc.PairStateInteractions(a, 40, 0, .5, 40, 0, .5, .5, .5)
+    p.defineBasis(0, 0, 2, 3, 25e9)
+    drive = [39, 1, 1.5, 0.5, 0]
+    R = np.array([1.5, 3.0, 6.0])
+    k = 30
+    p.diagonalise(R, k, drivingFromState=drive)
+    np.savez_compressed(os.path.join(GOLD, "pair_driving_golden.npz"),
+                        ctor=np.array([40, 0, .5, 40, 0, .5, .5, .5]), basis=np.array([0, 0, 2, 3, 25e9]),
+                        drive=np.array(drive, dtype=float), r=np.array(p.r), k=k, y=np.array(p.y),
+                        highlight=np.array(p.highlight), maxCoupling=p.maxCoupling,
+                        maxCoupledStateIndex=p.maxCoupledStateIndex, N=len(p.basisStates))
+    print("pair driving golden: N", len(p.basisStates), "maxCoupling", p.maxCoupling)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -354,3 +381,5 @@ if __name__ == "__main__":
         gen_pair(arc, big=True)
     if "divalent" in what:
         gen_divalent(arc)
+    if "driving" in what:
+        gen_driving(arc)
