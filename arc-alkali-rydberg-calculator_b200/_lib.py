@@ -46,7 +46,7 @@ _SIGNATURES = {
                                     c_i64, c_i32]),
     "arcb200_pair_sweep": (c_int, [c_int, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp,
                                    c_i32, c_dbl, c_i32, c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp,
-                                   c_vp, c_vp, c_i64, c_i32]),
+                                   c_vp, c_vp, c_vp, c_i64, c_i32]),
     "arcb200_scatter_coo": (c_int, [c_int, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_syevd_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                                       c_i64]),

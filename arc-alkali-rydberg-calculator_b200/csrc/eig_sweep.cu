@@ -213,6 +213,54 @@ __global__ void __launch_bounds__(256) epilogue_kernel(
         for (int t = kk; t < topk; ++t) { comp_c[orow * topk + t] = 0.0; comp_i[orow * topk + t] = -1; }
 }
 
+// ---------------------------------------------------------------- adiabatic overlaps
+// O[t][i][j] = ( v_t,i . v_(t-1),j )^2 between the selected eigenvectors of consecutive sweep
+// points (calculations_atom_pairstate.py:3462-3468).  One CTA per 16x16 output tile.
+__global__ void __launch_bounds__(256) overlap_kernel(
+    int N, int Npad, const double *base, size_t slot, size_t oQ, const int32_t *__restrict__ sel0,
+    int k, const double *__restrict__ prevZ /* N x k, ld N, for matrix 0 (or null) */,
+    double *__restrict__ ov, int point0)
+{
+    const int mat = blockIdx.z;
+    const double *Zc = base + (size_t)mat * slot + oQ + (size_t)sel0[mat] * Npad;
+    const double *Zp;
+    int ldp;
+    if (mat == 0) {
+        if (!prevZ) { Zp = Zc; ldp = Npad; }          // first point: overlap with itself
+        else { Zp = prevZ; ldp = N; }
+    } else {
+        Zp = base + (size_t)(mat - 1) * slot + oQ + (size_t)sel0[mat - 1] * Npad;
+        ldp = Npad;
+    }
+    __shared__ double A[16][65], B[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.x * 16, j0 = blockIdx.y * 16;
+    double acc = 0.0;
+    for (int r0 = 0; r0 < N; r0 += 64) {
+        for (int t = threadIdx.x; t < 16 * 64; t += 256) {
+            const int c = t >> 6, r = r0 + (t & 63);
+            A[c][t & 63] = (r < N && i0 + c < k) ? Zc[r + (size_t)(i0 + c) * Npad] : 0.0;
+            B[c][t & 63] = (r < N && j0 + c < k) ? Zp[r + (size_t)(j0 + c) * ldp] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int r = 0; r < 64; ++r) acc += A[tx][r] * B[ty][r];
+        __syncthreads();
+    }
+    if (i0 + tx < k && j0 + ty < k)
+        ov[((size_t)(point0 + mat) * k + (i0 + tx)) * k + (j0 + ty)] = acc * acc;
+}
+
+__global__ void save_window_kernel(int N, int Npad, const double *base, size_t slot, size_t oQ,
+                                   const int32_t *__restrict__ sel0, int k, int mat, double *out)
+{
+    const double *Z = base + (size_t)mat * slot + oQ + (size_t)sel0[mat] * Npad;
+    const size_t total = (size_t)N * k;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x)
+        out[e] = Z[(e % N) + (e / N) * Npad];
+}
+
 int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma,
                 cudaStream_t st, int *launches)
 {
@@ -283,7 +331,8 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
                                   const double *d_R, int32_t k, double sigma, int32_t opi,
                                   const double *d_drive_w, int32_t topk, double contrib_max,
                                   double *d_y, double *d_hl, double *d_comp_c,
-                                  int32_t *d_comp_i, void *d_work, int64_t wbytes, int32_t batch)
+                                  int32_t *d_comp_i, double *d_overlap, void *d_work,
+                                  int64_t wbytes, int32_t batch)
 {
     if (nR <= 0) return 0;
     if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
@@ -295,6 +344,12 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
     const WorkView W = carve(d_work, L, batch);
     const int ntiles = L.NB * (L.NB + 1) / 2;
     int launches = 0;
+    // eigenvector window of the last point of the previous batch (for the overlaps)
+    double *prevZ = (double *)((char *)d_work + work_bytes(L, batch));
+    if (d_overlap && (int64_t)(work_bytes(L, batch) + (size_t)N * k * sizeof(double)) > wbytes) {
+        arcb200_set_error("workspace too small for overlaps (add N*k doubles)");
+        return -1;
+    }
     for (int p0 = 0; p0 < nR; p0 += batch) {
         const int nmat = min(batch, nR - p0);
         assemble_pair_kernel<<<dim3(ntiles, nmat), 256, 0, st>>>(
@@ -306,6 +361,14 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
             N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w, topk,
             contrib_max, d_y, d_hl, d_comp_c, d_comp_i, p0);
         ++launches;
+        if (d_overlap) {
+            overlap_kernel<<<dim3((k + 15) / 16, (k + 15) / 16, nmat), 256, 0, st>>>(
+                N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, p0 == 0 ? nullptr : prevZ,
+                d_overlap, p0);
+            save_window_kernel<<<148, 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0,
+                                                    k, nmat - 1, prevZ);
+            launches += 2;
+        }
     }
     ARCB200_LAUNCH_CHECK("pair sweep");
     return launches;

@@ -442,6 +442,36 @@ class PairStateInteractions:
             s += ",%s %d\\rangle" % (printStateStringLatex(n2, l2, j2, s=self.s2), round(mj2))
         return s
 
+    @staticmethod
+    def _adiabatic_sort(res):
+        """Re-order every point's eigenpairs so that index i follows the state adiabatically
+        (calculations_atom_pairstate.py:3452-3492): greedy assignment by decreasing squared
+        overlap with the previous point's (already re-ordered) eigenvectors.  The overlaps of
+        the raw eigenvector sets come from the GPU (res.overlap); the permutations compose
+        sequentially on the host."""
+        nR, k = res.y.shape
+        prev = np.arange(k)                       # position -> raw index at the previous point
+        for t in range(nR):
+            S = res.overlap[t][:, prev]           # S[i, c] = overlap(raw i at t, position c at t-1)
+            order_flat = np.argsort(S.ravel())
+            rows_, cols_ = np.unravel_index(order_flat, (k, k))
+            rowPicked = np.zeros(k, dtype=bool)
+            colPicked = np.zeros(k, dtype=bool)
+            perm = np.zeros(k, dtype=np.int64)
+            j, done = k * k - 1, 0
+            while done < k:
+                while rowPicked[rows_[j]] or colPicked[cols_[j]]:
+                    j -= 1
+                rowPicked[rows_[j]] = True
+                colPicked[cols_[j]] = True
+                perm[cols_[j]] = rows_[j]
+                done += 1
+            res.y[t] = res.y[t][perm]
+            res.hl[t] = res.hl[t][perm]
+            res.comp_c[t] = res.comp_c[t][perm]
+            res.comp_i[t] = res.comp_i[t][perm]
+            prev = perm
+
     def device_operators(self):
         """matDiagonal and matR staged on the GPU (dense), built once per defineBasis."""
         if self._ops is None:
@@ -455,11 +485,6 @@ class PairStateInteractions:
                     eigenstateDetuning=0.0, sortEigenvectors=False, progressOutput=False,
                     debugOutput=False, batch=None):
         """calculations_atom_pairstate.py:3246-3522."""
-        if sortEigenvectors:
-            raise NotImplementedError(
-                "sortEigenvectors=True couples consecutive R points "
-                "(calculations_atom_pairstate.py:3452-3492); not available on the batched "
-                "GPU path")
         self.r = np.sort(rangeR)[::-1]
         dimension = len(self.basisStates)
         self.noOfEigenvectors = noOfEigenvectors
@@ -495,9 +520,11 @@ class PairStateInteractions:
         ops = self.device_operators()
         res = _sweep.pair_sweep(ops, self.r, noOfEigenvectors, eigenstateDetuning * 1.0e-9,
                                 self.originalPairStateIndex, drive_w=drive_w, topk=4,
-                                contrib_max=0.95, batch=batch)
+                                contrib_max=0.95, batch=batch, want_overlap=bool(sortEigenvectors))
         self.last_sweep = res
         self.gpu_kernel_launches += res.kernel_launches
+        if sortEigenvectors:
+            self._adiabatic_sort(res)
         self.y = [res.y[i] for i in range(len(self.r))]
         self.highlight = [res.hl[i] for i in range(len(self.r))]
         self.composition = PairCompositionView(self, res.comp_c, res.comp_i)

@@ -63,7 +63,8 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
 
 
 class SweepResult:
-    __slots__ = ("y", "hl", "comp_c", "comp_i", "kernel_launches", "h2d_bytes", "d2h_bytes")
+    __slots__ = ("y", "hl", "comp_c", "comp_i", "kernel_launches", "h2d_bytes", "d2h_bytes",
+                 "overlap")
 
 
 def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
@@ -147,7 +148,7 @@ class PairOperators:
 
 
 def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max=0.95, batch=None,
-               distributed=True, to_host=True):
+               distributed=True, to_host=True, want_overlap=False):
     """k eigenpairs nearest sigma of H(R) for every R (already sorted by the caller,
     calculations_atom_pairstate.py:3307, 3425-3520)."""
     import torch
@@ -158,9 +159,14 @@ def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max
     nR_all = len(rangeR)
     rank, world = dist_info() if distributed else (0, 1)
     lo, hi = shard_bounds(nR_all, rank, world)
+    # overlaps chain consecutive points: a shard also solves the point before its first one
+    # (one redundant solve per rank instead of a peer-to-peer exchange of N x k eigenvectors)
+    lead = 1 if (want_overlap and lo > 0 and hi > lo) else 0
+    lo -= lead
     nR = hi - lo
     N = ops.N
     res = SweepResult()
+    res.overlap = None
     d_R = torch.as_tensor(rangeR[lo:hi].copy()).to(dev)
     d_w = None
     if drive_w is not None:
@@ -170,23 +176,30 @@ def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max
     hl = torch.empty((nR, k), dtype=torch.float64, device=dev)
     comp_c = torch.zeros((nR, k, max(topk, 1)), dtype=torch.float64, device=dev)
     comp_i = torch.full((nR, k, max(topk, 1)), -1, dtype=torch.int32, device=dev)
+    ov = torch.empty((nR, k, k), dtype=torch.float64, device=dev) if want_overlap else None
     if nR > 0:
         b = _pick_batch(N, nR, k, device, batch)
-        wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, k))
+        wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, k)) + (N * k * 8 + 256 if want_overlap else 0)
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         rc = lib.arcb200_pair_sweep(device, _lib.stream_ptr(device), N, _lib.ptr(ops.d_h0),
                                     len(ops.d_M), _lib.ptr(ops.d_Mptrs), nR, _lib.ptr(d_R),
                                     int(k), float(sigma_ghz), int(opi), _lib.ptr(d_w),
                                     int(topk), float(contrib_max), _lib.ptr(y), _lib.ptr(hl),
                                     _lib.ptr(comp_c),
-                                    _lib.ptr(comp_i), _lib.ptr(work), wbytes, b)
+                                    _lib.ptr(comp_i), _lib.ptr(ov), _lib.ptr(work), wbytes, b)
         _lib.check(rc, "arcb200_pair_sweep")
         res.kernel_launches = rc
     else:
         res.kernel_launches = 0
+    if lead:      # drop the redundant leading point (its overlap row belongs to the previous rank)
+        y, hl, comp_c, comp_i, ov = y[1:], hl[1:], comp_c[1:], comp_i[1:], ov[1:]
     if world > 1:
         y, hl = gather_rows(y, nR_all), gather_rows(hl, nR_all)
         comp_c, comp_i = gather_rows(comp_c, nR_all), gather_rows(comp_i, nR_all)
+        if ov is not None:
+            ov = gather_rows(ov, nR_all)
+    if ov is not None:
+        res.overlap = ov.cpu().numpy() if to_host else ov
     if to_host:
         res.y, res.hl = y.cpu().numpy(), hl.cpu().numpy()
         res.comp_c, res.comp_i = comp_c.cpu().numpy(), comp_i.cpu().numpy()

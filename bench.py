@@ -382,17 +382,17 @@ def run_reference(args):
     # committed fixture when there is no GPU; with a GPU, from our own defineBasis
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    # UNTIMED set-up: the operators of the workload.  With a GPU they come from our
-    # defineBasis; without one the radial table is computed by the oracle on the host.
-    import torch
-    if torch.cuda.is_available():
-        calc = build_c3()
-    else:
-        import arc_b200
-        from oracle.host_radial import patch_atom_with_oracle
-        calc = arc_b200.PairStateInteractions(patch_atom_with_oracle(arc_b200.Rubidium()),
-                                              60, 0, .5, 60, 0, .5, .5, .5)
-        calc.defineBasis(0., 0., 5, 5, 25e9)
+    # UNTIMED set-up: the operators of the workload, built WITHOUT the GPU: host logic of
+    # defineBasis + radial elements from the oracle (the reference's own C Numerov when
+    # oracle/_ref is present), parallel over the host cores.
+    import arc_b200
+    from oracle.host_radial import patch_atom_with_oracle
+    t0 = time.time()
+    calc = arc_b200.PairStateInteractions(patch_atom_with_oracle(arc_b200.Rubidium(), procs=cores),
+                                          60, 0, .5, 60, 0, .5, .5, .5)
+    calc.defineBasis(0., 0., 5, 5, 25e9)
+    sys.stderr.write("reference arm: operators built on the host in %.1f s (N=%d)\n"
+                     % (time.time() - t0, len(calc.basisStates)))
     procs = min(cores, args.ref_procs or cores)
     nR = procs * max(1, args.ref_points_per_proc)
     ts = []

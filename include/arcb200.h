@@ -141,6 +141,10 @@ int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0d
  *   H = diag(h0) + sum_o M_o / (R*1e-6)^(3+o)      (M_o dense N x N, o < norders)
  * d_M = DEVICE array of norders device pointers to the dense row-major M_o.
  * k eigenpairs nearest sigma (GHz), ascending; hl/comp as above (topk entries).
+ * d_overlap (optional, nR x k x k): squared overlaps (v_t,i . v_(t-1),j)^2 between the selected
+ * eigenvectors of consecutive points, the input of the reference's adiabatic re-ordering
+ * (sortEigenvectors, calculations_atom_pairstate.py:3452-3492); point 0 overlaps with itself.
+ * When given, the workspace must hold N*k extra doubles.
  * Replaces the loop body of PairStateInteractions.diagonalise
  * (calculations_atom_pairstate.py:3425-3520; scipy eigsh at 3444-3450). */
 int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
@@ -148,7 +152,7 @@ int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0di
                        const double *d_R, int32_t k, double sigma, int32_t opi,
                        const double *d_drive_w, int32_t topk, double contrib_max,
                        double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
-                       void *d_work, int64_t work_bytes, int32_t batch);
+                       double *d_overlap, void *d_work, int64_t work_bytes, int32_t batch);
 
 /* Sparse (COO) -> dense scatter used to stage matR[o] on the device
  * (the reference keeps matR as scipy CSR, calculations_atom_pairstate.py:3230-3239). */

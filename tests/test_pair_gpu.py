@@ -92,4 +92,41 @@ def test_pair_c5_class_large_basis():
     w = np.linalg.eigvalsh(H)
     sel = np.sort(np.argsort(np.abs(w), kind="stable")[:250])
     assert np.abs(calc.y[0] - w[sel]).max() <= 1e-9 * np.abs(w).max()
-    assert abs(np.sum(calc.highlight[0]) - 1.0) < 0.5      # a fraction of the pair state is in the window
+    hs = float(np.sum(calc.highlight[0]))
+    assert 0.0 <= hs <= 1.0 + 1e-9                         # admixture of the pair state inside the window
+
+
+def test_pair_sort_eigenvectors_matches_reference(gold_dir):
+    """sortEigenvectors=True: adiabatic re-ordering (calculations_atom_pairstate.py:3452-3492)."""
+    g = np.load(os.path.join(gold_dir, "pair_sorted_golden.npz"))
+    import arc_b200
+    c, b = g["ctor"], g["basis"]
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]))
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]))
+    assert len(calc.basisStates) == int(g["N"])
+    calc.diagonalise(g["r"], int(g["k"]), sortEigenvectors=True)
+    y, gy = np.array(calc.y), g["y"]
+    scale = np.abs(gy).max()
+    # same multiset of energies at every point -- except possibly at the window EDGE: ARPACK
+    # (tol=1e-6) cannot resolve a near-degenerate cluster that straddles the k-th nearest
+    # eigenvalue and then returns the next level instead (seen at R=1.2 um: a 4-fold cluster at
+    # |lambda|=5.008 GHz, the reference finds 2 of it + the level at 5.212; the dense solver
+    # returns the true 20 nearest).  Interior eigenvalues must agree to 1e-7.
+    for t in range(len(gy)):
+        a_, b_ = np.sort(y[t]), np.sort(gy[t])
+        edge = 0.97 * min(np.abs(a_).max(), np.abs(b_).max())
+        ai, bi = a_[np.abs(a_) < edge], b_[np.abs(b_) < edge]
+        assert len(ai) == len(bi) and len(ai) >= len(a_) - 4
+        assert np.abs(ai - bi).max() <= 1e-7 * scale
+    # adiabatic tracking: column i follows the same curve as the reference's column i, up to
+    # swaps inside near-degenerate clusters (eigenvectors there are arbitrary)
+    close = np.abs(y - gy) <= 1e-6 * scale
+    assert close.mean() > 0.9
+    # the state with the largest admixture of the pair state is tracked identically
+    j = np.argmax(g["highlight"][0])
+    assert np.abs(y[:, j] - gy[:, j]).max() <= 1e-6 * scale
+    assert np.abs(np.array(calc.highlight)[:, j] - g["highlight"][:, j]).max() <= 1e-5
+    # unsorted run returns ascending rows; the sorted run generally does not
+    calc.diagonalise(g["r"], int(g["k"]))
+    assert np.all(np.diff(np.array(calc.y), axis=1) >= 0)

@@ -364,6 +364,21 @@ def gen_driving(arc):
     print("pair driving golden: N", len(p.basisStates), "maxCoupling", p.maxCoupling)
 
 
+def gen_sorted(arc):
+    """sortEigenvectors=True (adiabatic re-ordering, calculations_atom_pairstate.py:3452-3492)."""
+    a = arc.Rubidium()
+    p = arc.PairStateInteractions(a, 60, 0, .5, 60, 0, .5, .5, .5)
+    p.defineBasis(0, 0, 2, 3, 8e9)
+    R = np.linspace(1.2, 8.0, 24)
+    k = 20
+    p.diagonalise(R, k, sortEigenvectors=True)
+    np.savez_compressed(os.path.join(GOLD, "pair_sorted_golden.npz"),
+                        ctor=np.array([60, 0, .5, 60, 0, .5, .5, .5]), basis=np.array([0, 0, 2, 3, 8e9]),
+                        r=np.array(p.r), k=k, y=np.array(p.y), highlight=np.array(p.highlight),
+                        N=len(p.basisStates))
+    print("pair sorted golden: N", len(p.basisStates), np.array(p.y).shape)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -383,3 +398,5 @@ if __name__ == "__main__":
         gen_divalent(arc)
     if "driving" in what:
         gen_driving(arc)
+    if "sorted" in what:
+        gen_sorted(arc)
