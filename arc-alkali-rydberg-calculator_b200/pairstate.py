@@ -207,6 +207,107 @@ class PairStateInteractions:
         elem, terms = af
         return elem * sum(f * np.kron(A, B) for f, A, B in terms)
 
+    def _isCoupled(self, n, l, j, nn, ll, jj, n1, l1, j1, n2, l2, j2, limit):
+        """Scalar form of calculations_atom_pairstate.py:625-710 (returns c1+c2 or False)."""
+        if not (abs(self._getEnergyDefect(n, l, j, nn, ll, jj, n1, l1, j1, n2, l2, j2)) / C_h < limit):
+            return False
+        if n == n1 and nn == n2 and l == l1 and ll == l2 and j == j1 and jj == j2:
+            return False
+
+        def forb(dl, ja, jb):
+            return dl != 1 and ((abs(ja - 0.5) < 0.1 and abs(jb - 0.5) < 0.1)
+                                or (abs(ja) < 0.1 and abs(jb - 1) < 0.1)
+                                or (abs(ja - 1) < 0.1 and abs(jb) < 0.1))
+        if forb(abs(l1 - l), j, j1) or forb(abs(l2 - ll), jj, j2):
+            return False
+        if (abs(j) < 0.1 and abs(j1) < 0.1) or (abs(jj) < 0.1 and abs(j2) < 0.1):
+            return False
+        if (abs(l) < 0.1 and abs(l1) < 0.1) or (abs(ll) < 0.1 and abs(l2) < 0.1):
+            return False
+        c1 = _coupling_order(l, j, l1, j1, self.interactionsUpTo)
+        c2 = _coupling_order(ll, jj, l2, j2, self.interactionsUpTo)
+        if c1 == 0 or c2 == 0:
+            return False
+        return c1 + c2
+
+    def getC6perturbatively(self, theta, phi, nRange, energyDelta, degeneratePerturbation=False):
+        """C6 from second-order perturbation theory, GHz um^6
+        (calculations_atom_pairstate.py:1144-1440).  The radial elements of all intermediate
+        pair states come from one batched GPU run; the final (2j+1)(2jj+1) eigenproblem runs on
+        the GPU eigensolver."""
+        if abs(phi) >= 1e-9:
+            raise NotImplementedError("phi != 0 makes the interaction matrix complex-Hermitian")
+        wgd = WignerDmatrix(theta, phi)
+        Lmod2 = (self.l + self.ll) % 2
+        lmin1 = self.l - 1 if self.l - 1 >= 0 else 1
+        lmin2 = self.ll - 1 if self.ll - 1 >= 0 else 1
+        dim = round((2 * self.j + 1) * (2 * self.jj + 1))
+        inter = np.zeros((dim, dim))
+        cand = []
+        for n1 in range(max(self.n - nRange, 1), self.n + nRange + 1):
+            for n2 in range(max(self.nn - nRange, 1), self.nn + nRange + 1):
+                for l1 in range(lmin1, min(self.l + 2, n1), 2):
+                    for l2 in range(lmin2, min(self.ll + 2, n2), 2):
+                        if (l1 + l2) % 2 != Lmod2:
+                            continue
+                        j1 = l1 - self.s1
+                        while j1 < -0.1:
+                            j1 += 2 * self.s1
+                        while j1 <= l1 + self.s1 + 0.1:
+                            j2 = l2 - self.s2
+                            while j2 < -0.1:
+                                j2 += 2 * self.s2
+                            while j2 <= l2 + self.s2 + 0.1:
+                                coupled = self._isCoupled(self.n, self.l, self.j, self.nn, self.ll,
+                                                          self.jj, n1, l1, j1, n2, l2, j2, energyDelta)
+                                if (coupled and (not (self.interactionsUpTo == 1) or (Lmod2 == ((l1 + l2) % 2)))
+                                        and (n1 >= self.atom1.groundStateN or [n1, l1, j1] in self.atom1.extraLevels)
+                                        and (n2 >= self.atom2.groundStateN or [n2, l2, j2] in self.atom2.extraLevels)):
+                                    cand.append((n1, l1, j1, n2, l2, j2, coupled))
+                                j2 = j2 + 1.0
+                            j1 = j1 + 1.0
+        # one GPU batch per atom for all intermediate states
+        for atom, spin, mine, col in ((self.atom1, self.s1, (self.n, self.l, self.j), 0),
+                                      (self.atom2, self.s2, (self.nn, self.ll, self.jj), 3)):
+            dip, quad = [], []
+            for c in cand:
+                other = (c[col], c[col + 1], c[col + 2])
+                order = _coupling_order(mine[1], mine[2], other[1], other[2], self.interactionsUpTo)
+                (dip if order == 1 else quad).append(mine + other)
+            before = atom.gpu_kernel_launches
+            if getattr(atom, "divalent", False):
+                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad, s=spin)
+            else:
+                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad)
+            self.gpu_kernel_launches += atom.gpu_kernel_launches - before
+        a0 = physical_constants["Bohr radius"][0]
+        for (n1, l1, j1, n2, l2, j2, coupled) in cand:
+            defect = self._getEnergyDefect(self.n, self.l, self.j, self.nn, self.ll, self.jj,
+                                           n1, l1, j1, n2, l2, j2) / C_h * 1.0e-9          # GHz
+            if abs(defect) < 1e-10:
+                raise ValueError("The requested pair-state is dipole coupled resonatly (energy "
+                                 "defect = 0) to other pair-states. Aborting pertubative calculation.")
+            r1 = self.atom1.getRadialCoupling(self.n, self.l, self.j, n1, l1, j1, s=self.s1)
+            r2 = self.atom2.getRadialCoupling(self.nn, self.ll, self.jj, n2, l2, j2, s=self.s2)
+            strength = (C_e ** 2 / (4.0 * pi * epsilon_0) * r1 * r2 * a0 ** coupled) \
+                * (1.0e-9 * (1.0e6) ** 3 / C_h)                                          # GHz um^3
+            d = self._getAngularMatrix_M(self.l, self.j, self.ll, self.jj, l1, j1, l2, j2)
+            inter += d.T.dot(d) * abs(strength) ** 2 / defect
+        rot = np.kron(wgd.get(self.j), wgd.get(self.jj))
+        inter = (rot.dot(inter.dot(rot.conj().T))).real
+        inter = 0.5 * (inter + inter.T)
+        value, vecs = _sweep.syevd_batched(inter, device=getattr(self.atom1, "device", None))
+        self.gpu_kernel_launches += 1
+        value, vectors = value[0], vecs[0].T
+        state = np.zeros(dim)
+        state[round(self.j + self.m1) * round(2 * self.jj + 1) + round(self.jj + self.m2)] = 1.0
+        if not degeneratePerturbation:
+            for i, v in enumerate(vectors):
+                if abs(np.vdot(v, state)) > 1 - 1e-9:
+                    return value[i]
+            return float(state.dot(inter.dot(state)))
+        return np.real(value), vectors
+
     # ------------------------------------------------------------------ channels
     def _makeRawMatrix2(self, n, l, j, nn, ll, jj, k, lrange, limit, limitBasisToMj,
                         progressOutput=False, debugOutput=False):

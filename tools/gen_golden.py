@@ -379,6 +379,26 @@ def gen_sorted(arc):
     print("pair sorted golden: N", len(p.basisStates), np.array(p.y).shape)
 
 
+def gen_c6(arc):
+    """getC6perturbatively known answers (calculations_atom_pairstate.py:1144-1440)."""
+    out = []
+    k = arc.Potassium()
+    out.append({"atom": "Potassium39", "ctor": [66, 0, .5, 66, 0, .5, .5, .5], "args": [0, 0, 5, 30e9],
+                "value": float(arc.PairStateInteractions(k, 66, 0, .5, 66, 0, .5, .5, .5).getC6perturbatively(0, 0, 5, 30e9)),
+                "pin": "test/test_pairstate.py:4-10 (-265 +- 1)"})
+    rb = arc.Rubidium()
+    out.append({"atom": "Rubidium", "ctor": [60, 0, .5, 60, 0, .5, .5, .5], "args": [0, 0, 5, 25e9],
+                "value": float(arc.PairStateInteractions(rb, 60, 0, .5, 60, 0, .5, .5, .5).getC6perturbatively(0, 0, 5, 25e9)),
+                "pin": "doc/Rydberg_atoms_a_primer_notebook.ipynb:1710 (-138.88... sign per ARC)"})
+    for th in (0.0, 0.7, 1.5):
+        out.append({"atom": "Rubidium", "ctor": [60, 2, 2.5, 60, 2, 2.5, 2.5, 2.5], "args": [th, 0, 5, 25e9],
+                    "value": float(arc.PairStateInteractions(rb, 60, 2, 2.5, 60, 2, 2.5, 2.5, 2.5).getC6perturbatively(th, 0, 5, 25e9)),
+                    "pin": "live reference"})
+    with open(os.path.join(GOLD, "c6_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("c6 golden", [(o["atom"], o["args"][0], o["value"]) for o in out])
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -400,3 +420,5 @@ if __name__ == "__main__":
         gen_driving(arc)
     if "sorted" in what:
         gen_sorted(arc)
+    if "c6" in what:
+        gen_c6(arc)
