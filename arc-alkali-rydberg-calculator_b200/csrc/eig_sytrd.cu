@@ -19,6 +19,7 @@
 //   once per CTA (conflict-free stride 36), A fragments come from the warp's own rows.
 // Vectors are exchanged through L2 (ld.global.cg) between cluster barriers.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "eig.cuh"
 
 namespace cg = cooperative_groups;
@@ -511,7 +512,13 @@ int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *la
         return -1;
     }
     if (cluster <= 1) {
-        if (L.N <= 512 && nmat > 148) {
+        const char *ev = getenv("ARCB200_SYTRD_LEAN");      // tuning knob: force (1) / forbid (0)
+        // two matrices per SM (LEAN, <= 128 registers) whenever the batch has more matrices than
+        // SMs and two CTAs' shared memory fits: the HBM-bound symv sweeps of one matrix overlap
+        // the latency-bound row phases / DMMA update of the other (measured on B200, N=2363:
+        // 4.7 -> 4.1 ms per matrix)
+        const bool lean = ev ? (ev[0] == '1') : (nmat > 148 && 2 * smem <= 200 * 1024);
+        if (lean) {
             ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sytrd_kernel<false, true>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             sytrd_kernel<false, true><<<nmat, SY_THREADS, smem, st>>>(a);

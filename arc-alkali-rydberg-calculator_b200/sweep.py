@@ -47,7 +47,10 @@ def gather_rows(local, npoints, group=None):
 
 
 def _pick_batch(N, npoints, nvec, device, batch=None):
+    import os
     import torch
+    if batch is None and os.environ.get("ARCB200_BATCH"):      # tuning knob
+        batch = int(os.environ["ARCB200_BATCH"])
     if batch is not None:
         return max(1, min(int(batch), npoints))
     free, _total = torch.cuda.mem_get_info(device)
@@ -55,7 +58,8 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
     b = int(min(npoints, max(1, (0.6 * free) // per)))
     # one CTA (or a small cluster) per matrix: 148 matrices in flight fill the GPU
-    cap = 592 if N <= 512 else (296 if N <= 1024 else (148 if N <= 4096 else 18))
+    # (two per SM while two CTAs' shared memory fits, N <= ~4000)
+    cap = 592 if N <= 512 else (296 if N <= 4000 else (148 if N <= 4096 else 18))
     b = max(1, min(b, cap))
     # equal chunks: a nearly empty tail pass costs a full sweep latency
     nchunks = -(-npoints // b)

@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3"])
-    ap.add_argument("--points", type=int, default=148, help="R points per GPU per step")
+    ap.add_argument("--points", type=int, default=296, help="R points per GPU per step")
     ap.add_argument("--skip-sub", action="store_true", help="skip the c1/c2 sub-workloads")
     ap.add_argument("--cpu-pair-points", type=int, default=6)
     ap.add_argument("--cpu-radial-pairs", type=int, default=150)
