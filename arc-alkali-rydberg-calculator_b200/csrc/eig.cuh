@@ -12,12 +12,22 @@ struct EigLayout {
     int N, Npad, NB, nvec;
     // per-slot element offsets (in doubles) inside the slot
     size_t oA, oQ1, oQ2, oU, oWp, oVp, oTrans, oWdir, oD, oE, oTau, oScr, oTfac, oLam, oAux;
+    // two-stage path (eig_twostage.cu): compact band, bulge-chasing reflectors and their taus
+    size_t oBand, oV2, oTau2;
+    int two_stage;
     size_t slot_doubles;
     // int workspace per slot (in int32)
     size_t oPerm, oIdx, slot_ints;
 };
 
+constexpr int EIG_LDB = 72;         // leading dimension of the compact lower band (>= 2*32 + 1)
+
 static inline size_t eig_align(size_t x) { return (x + 31) & ~(size_t)31; }
+
+// Two-stage tridiagonalisation (dense -> band -> tridiagonal) for mid-sized matrices that are
+// solved one CTA per matrix; small matrices are latency bound either way and very large ones
+// need a whole cluster per matrix (one-stage kernel).  ARCB200_TWO_STAGE=0/1 overrides.
+int eig_use_two_stage(int N);
 
 static inline EigLayout eig_layout(int N, int nvec)
 {
@@ -31,7 +41,7 @@ static inline EigLayout eig_layout(int N, int nvec)
     L.oA = o;      o += np * np;
     L.oQ1 = o;     o += np * np;
     L.oQ2 = o;     o += np * np;
-    L.oU = o;      o += np * np;
+    L.oU = o;      o += np * (np + 64);             // also the row-major Z window of the Q2 pass
     L.oWp = o;     o += np * EIG_PB;
     L.oVp = o;     o += np * EIG_PB;
     L.oTrans = o;  o += (size_t)L.NB * np;
@@ -43,6 +53,13 @@ static inline EigLayout eig_layout(int N, int nvec)
     L.oTfac = o;   o += (size_t)L.NB * EIG_PB * EIG_PB;   // T factors of the block reflectors
     L.oLam = o;    o += np;                         // eigenvalues
     L.oAux = o;    o += 12 * np;                    // D&C vectors (z, dlamda, w, ...)
+    L.two_stage = eig_use_two_stage(N);
+    L.oBand = L.oV2 = L.oTau2 = o;
+    if (L.two_stage) {
+        L.oBand = o;   o += (size_t)EIG_LDB * (np + 64);
+        L.oV2 = o;     o += np * np;
+        L.oTau2 = o;   o += np * (size_t)(L.NB + 2);
+    }
     L.slot_doubles = eig_align(o);
     size_t oi = 0;
     L.oPerm = oi;  oi += 8 * np;
@@ -72,3 +89,9 @@ int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches, int s
 int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
               int *launches);
 int eig_pick_cluster(int N, int nmat);
+// two-stage variants: A -> band (V1 below the band, T factors in oTfac) -> (d, e) with the
+// bulge-chasing reflectors in oV2/oTau2; back-transformation Z = Q1 (Q2 Z)
+int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
+int eig_sb2st(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
+int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
+                 int *launches);

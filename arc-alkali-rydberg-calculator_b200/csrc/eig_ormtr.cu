@@ -21,13 +21,15 @@ struct OrmArgs {
     size_t oA, oTau, oTfac, oZ;
     int nsel;
     const int32_t *sel0;        // per matrix first selected column (or null -> 0)
+    int off;                    // reflector c has its implicit 1 at row c + off (1: sytrd, 32: sy2sb)
 };
 
-__device__ __forceinline__ double vval(const double *__restrict__ A, int lda, int N, int r, int c)
+__device__ __forceinline__ double vval(const double *__restrict__ A, int lda, int N, int r, int c,
+                                       int off)
 {
     // element r of Householder vector c
-    if (c > N - 2 || r <= c || r >= N) return 0.0;
-    if (r == c + 1) return 1.0;
+    if (c + off > N - 1 || r < c + off || r >= N) return 0.0;
+    if (r == c + off) return 1.0;
     return A[r + (size_t)c * lda];
 }
 
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(OT_THREADS) larft_kernel(OrmArgs a)
     for (int r0 = c0; r0 < N; r0 += 64) {
         for (int t = tid; t < 32 * 64; t += OT_THREADS) {
             const int col = t >> 6, rr = t & 63;
-            Vs[col][rr] = vval(A, lda, N, r0 + rr, c0 + col);
+            Vs[col][rr] = vval(A, lda, N, r0 + rr, c0 + col, a.off);
         }
         __syncthreads();
 #pragma unroll
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(OT_THREADS) larft_kernel(OrmArgs a)
         const int j = tid;
         for (int i = 0; i < 32; ++i) {
             const int c = c0 + i;
-            const double ti = (c <= N - 2) ? tau[c] : 0.0;
+            const double ti = (c + a.off <= N - 1) ? tau[c] : 0.0;
             double s = 0.0;
             if (j < i) {
                 for (int l = j; l < i; ++l) s += Ts[j][l] * G[l][i];
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_kernel(OrmArgs a)
 
     for (int b = a.NBR - 1; b >= 0; --b) {
         const int c0 = 32 * b;
-        const int rbeg = c0 + 1;                 // first row with a non-zero V entry
+        const int rbeg = c0 + a.off;             // first row with a non-zero V entry
         const int chunk0 = rbeg & ~31;
         for (int t = tid; t < 1024; t += OT_THREADS) Tsm[t >> 5][t & 31] = Tall[(size_t)b * 1024 + t];
         // ---------------- pass 1: W = V^T Z  (32 x 32), K = rows ----------------
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_kernel(OrmArgs a)
             const int r = r0 + lane;
 #pragma unroll 8
             for (int cc = 0; cc < 32; ++cc) {
-                Vs[wid][cc][lane] = vval(A, lda, N, r, c0 + cc);
+                Vs[wid][cc][lane] = vval(A, lda, N, r, c0 + cc, a.off);
                 Zs[wid][cc][lane] = (r < N && cc < ncol) ? Z[r + (size_t)cc * lda] : 0.0;
             }
             __syncwarp();
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_kernel(OrmArgs a)
             const int r = r0 + lane;
 #pragma unroll 8
             for (int cc = 0; cc < 32; ++cc) {
-                Vs[wid][cc][lane] = -vval(A, lda, N, r, c0 + cc);
+                Vs[wid][cc][lane] = -vval(A, lda, N, r, c0 + cc, a.off);
                 Zs[wid][cc][lane] = (r < N && cc < ncol) ? Z[r + (size_t)cc * lda] : 0.0;
             }
             __syncwarp();
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_smem_kernel(OrmArgs a)
 
     for (int b = a.NBR - 1; b >= 0; --b) {
         const int c0 = 32 * b;
-        const int chunk0 = (c0 + 1) & ~31;
+        const int chunk0 = (c0 + a.off) & ~31;
         for (int t = tid; t < 1024; t += OT_THREADS) Tsm[t >> 5][t & 31] = Tall[(size_t)b * 1024 + t];
         for (int t = tid; t < SW * TS; t += OT_THREADS) (&Wred[0][0])[t] = 0.0;
         // ---------------- pass 1: W = V^T Z ----------------
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_smem_kernel(OrmArgs a)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = r0 + 4 * ks + tig, c = c0 + 8 * i + grp;
-                    af[ks][i] = (top || r >= N || c > N - 2) ? vval(A, lda, N, r, c) : A[r + (size_t)c * lda];
+                    af[ks][i] = (top || r >= N || c + a.off > N - 1) ? vval(A, lda, N, r, c, a.off) : A[r + (size_t)c * lda];
                 }
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(OT_THREADS) ormtr_smem_kernel(OrmArgs a)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = r0 + 8 * i + grp, c = c0 + 4 * ks + tig;
-                    af[ks][i] = -((top || r >= N || c > N - 2) ? vval(A, lda, N, r, c) : A[r + (size_t)c * lda]);
+                    af[ks][i] = -((top || r >= N || c + a.off > N - 1) ? vval(A, lda, N, r, c, a.off) : A[r + (size_t)c * lda]);
                 }
             double c2[4][NT][2];
 #pragma unroll
@@ -386,11 +388,14 @@ int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cuda
     if (L.N < 3 || nsel <= 0) return 0;
     OrmArgs a;
     a.N = L.N; a.Npad = L.Npad;
-    a.NBR = (L.N - 1 + 31) / 32;
+    a.off = L.two_stage ? 32 : 1;
+    a.NBR = L.two_stage ? L.NB - 1 : (L.N - 1 + 31) / 32;
     a.base = S.dbl; a.slot = L.slot_doubles;
     a.oA = L.oA; a.oTau = L.oTau; a.oTfac = L.oTfac; a.oZ = L.oQ1;
     a.nsel = nsel; a.sel0 = d_sel0;
-    larft_kernel<<<dim3(a.NBR, nmat), OT_THREADS, 0, st>>>(a);
+    if (a.NBR <= 0) return 0;
+    // the band reduction (eig_twostage.cu) leaves its T factors in oTfac already
+    if (!L.two_stage) larft_kernel<<<dim3(a.NBR, nmat), OT_THREADS, 0, st>>>(a);
     // shared-memory resident slab when it fits (<= 200 KiB): widest slab first
     const size_t budget = 200 * 1024;
     auto fits = [&](int sw) {

@@ -265,12 +265,22 @@ int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma
                 cudaStream_t st, int *launches)
 {
     const EigLayout &L = W.S.L;
-    const int cluster = eig_pick_cluster(L.N, nmat);
-    int rc = eig_sytrd(W.S, nmat, cluster, st, launches);
+    int rc;
+    if (L.two_stage) {
+        rc = eig_sy2sb(W.S, nmat, st, launches);
+        if (rc) return rc;
+        rc = eig_sb2st(W.S, nmat, st, launches);
+    } else {
+        rc = eig_sytrd(W.S, nmat, eig_pick_cluster(L.N, nmat), st, launches);
+    }
     if (rc) return rc;
     rc = eig_stedc(W.S, nmat, st, launches, window ? nsel : 0, sigma, window ? W.sel0 : nullptr);
     if (rc) return rc;
     const int32_t *sel = window ? W.sel0 : nullptr;
+    if (L.two_stage) {
+        rc = eig_q2_apply(W.S, nmat, sel, nsel, st, launches);
+        if (rc) return rc;
+    }
     return eig_ormtr(W.S, nmat, sel, nsel, st, launches);
 }
 
@@ -419,13 +429,50 @@ extern "C" int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_
     const WorkView W = carve(d_work, L, batch);
     int launches = 0;
     load_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_A);
-    int rc = eig_sytrd(W.S, batch, cluster > 0 ? cluster : eig_pick_cluster(N, batch), st, &launches);
+    int rc;
+    if (L.two_stage && cluster <= 0) {
+        rc = eig_sy2sb(W.S, batch, st, &launches);
+        if (rc) return rc;
+        rc = eig_sb2st(W.S, batch, st, &launches);
+    } else {
+        rc = eig_sytrd(W.S, batch, cluster > 0 ? cluster : eig_pick_cluster(N, batch), st, &launches);
+    }
     if (rc) return rc;
     copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oD, d_d);
     copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oE, d_e);
     if (d_tau) copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oTau, d_tau);
     ARCB200_LAUNCH_CHECK("sytrd_batched");
     return launches + 3;
+}
+
+// band after stage 1 of the two-stage reduction: d_band[b][j][d] = B[j+d][j], d = 0..32
+__global__ void copy_band_kernel(int N, const double *base, size_t slot, size_t off, double *out)
+{
+    const int mat = blockIdx.y;
+    const double *Bd = base + (size_t)mat * slot + off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * 33; i += gridDim.x * blockDim.x) {
+        const int j = i / 33, d = i % 33;
+        out[(size_t)mat * N * 33 + i] = Bd[d + (size_t)j * EIG_LDB];
+    }
+}
+
+extern "C" int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_t batch,
+                                     const double *d_A, double *d_band, void *d_work,
+                                     int64_t wbytes)
+{
+    ARCB200_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const EigLayout L = eig_layout(N, N);
+    if (!L.two_stage) { arcb200_set_error("sy2sb_batched: N=%d is outside the two-stage range", N); return -1; }
+    if ((int64_t)work_bytes(L, batch) > wbytes) { arcb200_set_error("workspace too small"); return -1; }
+    const WorkView W = carve(d_work, L, batch);
+    int launches = 0;
+    load_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_A);
+    int rc = eig_sy2sb(W.S, batch, st, &launches);
+    if (rc) return rc;
+    copy_band_kernel<<<dim3(16, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oBand, d_band);
+    ARCB200_LAUNCH_CHECK("sy2sb_batched");
+    return launches + 2;
 }
 
 extern "C" int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,

@@ -257,6 +257,27 @@ def sytrd_batched(A, cluster=0, device=None):
     return [o.cpu().numpy() for o in outs]
 
 
+def sy2sb_batched(A, device=None):
+    """Stage 1 of the two-stage path only: the symmetric band (width 32) each A[b] is reduced
+    to, returned as band[b, j, d] = B[j+d, j]."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[None]
+    batch, N, _ = A.shape
+    d_A = torch.as_tensor(A).to(dev)
+    band = torch.zeros((batch, N, 33), dtype=torch.float64, device=dev)
+    wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rc = lib.arcb200_sy2sb_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
+                                   _lib.ptr(band), _lib.ptr(work), wbytes)
+    _lib.check(rc, "arcb200_sy2sb_batched")
+    return band.cpu().numpy()
+
+
 def stedc_batched(d, e, device=None):
     """Stage 2 only: eigen-decomposition of symmetric tridiagonal matrices (d, e)."""
     import torch

@@ -180,6 +180,12 @@ int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
 int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
                           const double *d_d, const double *d_e, double *d_w, double *d_Q,
                           void *d_work, int64_t work_bytes);
+/* Stage 1 of the two-stage path alone (dense -> band of width 32, mid-sized N only; when the
+ * two-stage path is active arcb200_sytrd_batched with cluster = 0 runs both of its stages and
+ * returns the tridiagonal d, e; tau is then per band-reduction reflector).
+ * d_band[b][j][d] = B[j+d][j], d = 0..32 (batch x N x 33). */
+int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_t batch,
+                          const double *d_A, double *d_band, void *d_work, int64_t work_bytes);
 
 #ifdef __cplusplus
 }
