@@ -57,11 +57,32 @@ __device__ __forceinline__ void dmma_t(double &d0, double &d1, double a, double 
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async8_t(void *dst, const void *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async16_t(void *dst, const void *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all_t()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 1: dense -> band
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
+// WARPS = 8: one CTA per SM; WARPS = 4: two CTAs (two matrices) per SM, whose latency-bound
+// panel factorisations and tensor-bound updates overlap.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
 {
+    constexpr int NT = WARPS * 32;
+    constexpr int TSTR = 40;                         // per-warp transit tile [cc][TSTR] (column-major)
+    constexpr int UNI = WARPS * 32 * TSTR + 4608;    // transit tiles + operand tiles (doubles)
     const int mat = blockIdx.x;
     const int np = a.Npad, lda = a.Npad, NB = a.NB;
     double *slot = a.base + (size_t)mat * a.slot;
@@ -72,19 +93,30 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
     double *__restrict__ Tfac = slot + a.oTfac;
 
     extern __shared__ double sm[];
-    double *uni = sm;                                               // 8448 doubles (union)
-    double(*tileT)[32 * 33] = reinterpret_cast<double(*)[32 * 33]>(uni);           // [warp][j*33+l]
-    double(*Bs)[2][32][BSTR] = reinterpret_cast<double(*)[2][32][BSTR]>(uni);      // [buf][op][n][k]
-    double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + 8448);
-    double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + 8448 + 1056);
-    double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + 8448 + 2 * 1056);
-    double(*red)[32] = reinterpret_cast<double(*)[32]>(sm + 8448 + 3 * 1056);      // [warp][j]
-    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + 8448 + 3 * 1056 + 256); // [warp][j]
-    double *sred = sm + 8448 + 3 * 1056 + 512;                                     // [8] + alpha
-    double *taus = sred + 16;                                                      // [32]
+    double *uni = sm;
+    double(*Bs)[2][32][BSTR] = reinterpret_cast<double(*)[2][32][BSTR]>(uni + WARPS * 32 * TSTR);   // [buf][op][n][k]
+    double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + UNI);
+    double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
+    double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
+    double(*red)[WARPS][32] = reinterpret_cast<double(*)[WARPS][32]>(sm + UNI + 3 * 1056);   // [par][warp][j]
+    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 2 * WARPS * 32);  // [warp][j]
+    double(*hrow)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32); // [par][j]
+    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 64); // [par][warp], [par][15] = alpha
+    double *taus = sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 96;                       // [32]
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int grp = lane >> 2, tig = lane & 3;
+    double *Tw = uni + wid * (32 * TSTR);
+    // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
+    // tile: 16-byte pieces, whole 256-byte column segments per half warp
+    auto issue_tile = [&](int Ib, int Jb) {
+        const double *src = A + (size_t)(32 * Jb) * lda + 32 * Ib;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int pi = lane + 32 * k, cc = pi >> 4, ro = (pi & 15) * 2;
+            cp_async16_t(&Tw[cc * TSTR + ro], src + (size_t)cc * lda + ro);
+        }
+    };
 
     TSP_DECL
     for (int p = 0; p < NB - 1; ++p) {
@@ -94,92 +126,141 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
 
         // ---------------------------------------------------------------- panel QR
+        // Two phases per column c (c = -1: gather only), lane <-> row everywhere:
+        //   A  rows dealt to the warps: finalise column c (v = x * scale, beta on the diagonal),
+        //      apply H_c to column cn = c + 1 and gather its norm and pivot  -> block reduce
+        //   B  columns dealt to the warps (j = wid + WARPS k): apply H_c to the own columns j > cn
+        //      and gather g_j = sum_{r > rd+1} x_cn(r) x_j(r) and the pivot row, so that
+        //      tau' w'_j = tau' (x_j(rd+1) + scale' g_j) is known to the owner without another pass.
+        // Loads are issued in register batches ahead of the dependent stores.
         {
-            double ssq = 0.0;
-            for (int ch = wid; ch < nch; ch += TS_WARPS) {
-                const int r = m0 + 32 * ch + lane;
-                if (r > m0) { const double x = P[r]; ssq += x * x; }
-            }
-            ssq = warp_sum(ssq);
-            if (lane == 0) sred[wid] = ssq;
-            if (tid == 0) sred[8] = P[m0];
-        }
-        for (int c = 0; c < 32; ++c) {
-            __syncthreads();                                         // sync #1
-            const int rd = m0 + c;
-            double xn2 = 0.0;
+            constexpr int KO = 32 / WARPS;
+            double wreg[KO];
 #pragma unroll
-            for (int q = 0; q < TS_WARPS; ++q) xn2 += sred[q];
-            const double alpha = sred[8];
-            double tau = 0.0, beta = alpha, scale = 0.0;
-            if (rd < np - 1 && xn2 != 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
-            }
-            if (tid == 0) { tt[col0 + c] = tau; taus[c] = tau; }
-            // pass B: v, w_j = v^T P[:, j] (j > c)
-            double acc[32];
+            for (int k = 0; k < KO; ++k) wreg[k] = 0.0;
+            double tau = 0.0, scale = 0.0, beta = 0.0;
+            for (int c = -1; c < 32; ++c) {
+                const int rd = m0 + c, cn = c + 1, par = cn & 1;
+                // ---------------- phase A
+                double ssq = 0.0;
+                const double wcn = (c >= 0 && cn < 32) ? wv[c & 1][cn] : 0.0;
+                for (int ch0 = wid; ch0 < nch; ch0 += WARPS * 4) {
+                    double pc[4], pn[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-            for (int ch = wid; ch < nch; ch += TS_WARPS) {
-                const int r = m0 + 32 * ch + lane;
-                double v = 0.0;
-                if (r == rd) {
-                    v = 1.0;
-                    P[r + (size_t)c * lda] = beta;
-                } else if (r > rd) {
-                    v = P[r + (size_t)c * lda] * scale;
-                    P[r + (size_t)c * lda] = v;
-                }
-                Vp[(size_t)c * np + r] = v;
-                if (r >= rd) {
+                    for (int u = 0; u < 4; ++u) {
+                        const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
+                        pc[u] = (c >= 0 && ch < nch) ? P[r + (size_t)c * lda] : 0.0;
+                        pn[u] = (cn < 32 && ch < nch) ? P[r + (size_t)cn * lda] : 0.0;
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j > c) acc[j] += v * P[r + (size_t)j * lda];
-                }
-            }
-            double *mt = tileT[wid];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mt[j * 33 + lane] = acc[j];
-            __syncwarp();
-            double wpart = 0.0;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) wpart += mt[lane * 33 + l];
-            red[wid][lane] = wpart;
-            __syncthreads();                                         // sync #2
-            double wj = 0.0;
-#pragma unroll
-            for (int q = 0; q < TS_WARPS; ++q) wj += red[q][lane];
-            wv[wid][lane] = wj * tau;
-            __syncwarp();
-            // pass C: P[:, j] -= tau v w_j ; norm / pivot of the next column ride along
-            double ssq = 0.0;
-            for (int ch = wid; ch < nch; ch += TS_WARPS) {
-                const int r = m0 + 32 * ch + lane;
-                if (r >= rd) {
-                    const double v = Vp[(size_t)c * np + r];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j > c) {
-                            const double x = P[r + (size_t)j * lda] - v * wv[wid][j];
-                            P[r + (size_t)j * lda] = x;
-                            if (j == c + 1) {
+                    for (int u = 0; u < 4; ++u) {
+                        const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
+                        if (ch < nch) {
+                            double v = 0.0;
+                            if (c >= 0) {
+                                if (r == rd) {
+                                    v = 1.0;
+                                    P[r + (size_t)c * lda] = beta;
+                                } else if (r > rd) {
+                                    v = pc[u] * scale;
+                                    P[r + (size_t)c * lda] = v;
+                                }
+                                Vp[(size_t)c * np + r] = v;
+                            }
+                            if (cn < 32 && r >= rd) {
+                                double x = pn[u];
+                                if (c >= 0) {
+                                    x -= v * wcn;
+                                    P[r + (size_t)cn * lda] = x;
+                                }
+                                if (r == rd + 1) sred[par][15] = x;
                                 if (r > rd + 1) ssq += x * x;
-                                if (r == rd + 1) sred[8] = x;
                             }
                         }
                     }
                 }
+                if (cn >= 32) break;
+                ssq = warp_sum(ssq);
+                if (lane == 0) sred[par][wid] = ssq;
+                __syncthreads();                                     // #1
+                double xn2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < WARPS; ++q) xn2 += sred[par][q];
+                const double alpha = sred[par][15];
+                double tau_n = 0.0, beta_n = alpha, scale_n = 0.0;
+                if (rd + 1 < np - 1 && xn2 != 0.0) {
+                    beta_n = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                    tau_n = (beta_n - alpha) / beta_n;
+                    scale_n = 1.0 / (alpha - beta_n);
+                }
+                if (tid == 0) { tt[col0 + cn] = tau_n; taus[cn] = tau_n; }
+                // ---------------- phase B
+                double g[KO], h[KO];
+#pragma unroll
+                for (int k = 0; k < KO; ++k) g[k] = h[k] = 0.0;
+                double va[4], xa[4], oa[4][KO], vb[4], xb[4], ob[4][KO];
+                auto loadB = [&](int b, double(&vv)[4], double(&xx)[4], double(&oo)[4][KO]) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ch = 4 * b + u, r = m0 + 32 * ch + lane;
+                        const bool ok = ch < nch;
+                        vv[u] = (ok && c >= 0) ? Vp[(size_t)c * np + r] : 0.0;
+                        xx[u] = ok ? P[r + (size_t)cn * lda] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < KO; ++k) {
+                            const int j = wid + WARPS * k;
+                            oo[u][k] = (ok && j > cn) ? P[r + (size_t)j * lda] : 0.0;
+                        }
+                    }
+                };
+                auto compB = [&](int b, const double(&vv)[4], const double(&xx)[4], const double(&oo)[4][KO]) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ch = 4 * b + u, r = m0 + 32 * ch + lane;
+                        if (ch < nch && r >= rd) {
+                            const double xg = (r > rd + 1) ? xx[u] : 0.0;
+#pragma unroll
+                            for (int k = 0; k < KO; ++k) {
+                                const int j = wid + WARPS * k;
+                                if (j > cn) {
+                                    double x = oo[u][k];
+                                    if (c >= 0) {
+                                        x -= vv[u] * wreg[k];
+                                        P[r + (size_t)j * lda] = x;
+                                    }
+                                    g[k] += xg * x;
+                                    if (r == rd + 1) h[k] = x;
+                                }
+                            }
+                        }
+                    }
+                };
+                const int nbat = (nch + 3) / 4;
+                loadB(0, va, xa, oa);
+                for (int b = 0; b < nbat; b += 2) {
+                    if (b + 1 < nbat) loadB(b + 1, vb, xb, ob);
+                    compB(b, va, xa, oa);
+                    if (b + 1 < nbat) {
+                        if (b + 2 < nbat) loadB(b + 2, va, xa, oa);
+                        compB(b + 1, vb, xb, ob);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KO; ++k) {
+                    g[k] = warp_sum(g[k]);
+                    h[k] = __shfl_sync(ARCB200_FULL_MASK, h[k], cn & 31);   // row m0 + cn: chunk 0, lane cn
+                    wreg[k] = tau_n * (h[k] + scale_n * g[k]);
+                    if (lane == 0) wv[par][wid + WARPS * k] = wreg[k];
+                }
+                tau = tau_n; beta = beta_n; scale = scale_n;
+                __syncthreads();                                     // #2
             }
-            ssq = warp_sum(ssq);
-            if (lane == 0) sred[wid] = ssq;
         }
         __syncthreads();
         TSP(1)
 
         // ---------------------------------------------------------------- T factor
-        for (int t = tid; t < 1024; t += TS_THREADS) { G[t >> 5][t & 31] = 0.0; Ts[t >> 5][t & 31] = 0.0; }
+        for (int t = tid; t < 1024; t += NT) { G[t >> 5][t & 31] = 0.0; Ts[t >> 5][t & 31] = 0.0; }
         __syncthreads();
         {
             double acc[4][4][2];
@@ -187,7 +268,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            for (int ch = wid; ch < nch; ch += TS_WARPS) {
+            for (int ch = wid; ch < nch; ch += WARPS) {
                 const int r0 = m0 + 32 * ch;
                 double f[4][8];
 #pragma unroll
@@ -227,18 +308,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
             }
         }
         __syncthreads();
-        for (int t = tid; t < 1024; t += TS_THREADS) Tfac[(size_t)p * 1024 + t] = Ts[t >> 5][t & 31];
+        for (int t = tid; t < 1024; t += NT) Tfac[(size_t)p * 1024 + t] = Ts[t >> 5][t & 31];
 
         TSP(2)
         // ---------------------------------------------------------------- X = A22 V
+        // Row block i of X = sum_q Asym(i, q) V_q: warp <-> i (groups of WARPS block rows).  The
+        // stored tile (lower triangle; transposed use when q > i) arrives in the warp's transit
+        // tile by cp.async while the previous product runs; V_q is shared through shared memory.
         const int Jt = p + 1;
-        auto stageV = [&](int buf, int q) {
-            const int k = tid & 31, n0 = tid >> 5;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4)
-                Bs[buf][0][n0 + 8 * i4][k] = Vp[(size_t)(n0 + 8 * i4) * np + 32 * q + k];
-        };
-        for (int g0 = Jt; g0 < NB; g0 += TS_WARPS) {
+        constexpr int SV = 32 / WARPS;
+        for (int g0 = Jt; g0 < NB; g0 += WARPS) {
             const int i = g0 + wid;
             const bool act = i < NB;
             double acc[4][4][2];
@@ -246,27 +325,44 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            double fa[4][8], fn[4][8];
-            auto load_tile = [&](double(&f)[4][8], int q) {
-                // symmetric element (32 i + rr, 32 q + cc) from the lower triangle
+            auto fillV = [&](int buf, int q) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const int ri = 32 * i + 8 * x + grp, ci = 32 * q + 4 * ks + tig;
-                        const int hi = max(ri, ci), lo = min(ri, ci);
-                        f[x][ks] = __ldcg(&A[hi + (size_t)lo * lda]);
-                    }
+                for (int n = 0; n < SV; ++n)
+                    cp_async8_t(&Bs[buf][0][wid + WARPS * n][lane], &Vp[(size_t)(wid + WARPS * n) * np + 32 * q + lane]);
             };
             __syncthreads();
-            stageV(0, Jt);
-            if (act) load_tile(fa, Jt);
+            if (act) issue_tile(max(i, Jt), min(i, Jt));
+            fillV(0, Jt);
+            cp_async_wait_all_t();
             __syncthreads();
             for (int q = Jt; q < NB; ++q) {
                 const int buf = (q - Jt) & 1;
+                double fa[4][8];
+                if (act) {
+                    if (q < i) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = Tw[(4 * ks + tig) * TSTR + 8 * x + grp];
+                    } else if (q > i) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = Tw[(8 * x + grp) * TSTR + 4 * ks + tig];
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {
+                                const int rr = 8 * x + grp, cc = 4 * ks + tig;
+                                fa[x][ks] = (rr >= cc) ? Tw[cc * TSTR + rr] : Tw[rr * TSTR + cc];
+                            }
+                    }
+                }
+                __syncwarp();
                 if (q + 1 < NB) {
-                    stageV(buf ^ 1, q + 1);
-                    if (act) load_tile(fn, q + 1);
+                    if (act) issue_tile(max(i, q + 1), min(i, q + 1));
+                    fillV(buf ^ 1, q + 1);
                 }
                 if (act) {
 #pragma unroll
@@ -278,11 +374,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
                             for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x][ks], b);
                         }
                     }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) fa[x][ks] = fn[x][ks];
                 }
+                cp_async_wait_all_t();
                 __syncthreads();
             }
             if (act) {
@@ -299,7 +392,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         TSP(3)
 
         // ---------------------------------------------------------------- W
-        for (int t = tid; t < 1024; t += TS_THREADS) G[t >> 5][t & 31] = 0.0;
+        for (int t = tid; t < 1024; t += NT) G[t >> 5][t & 31] = 0.0;
         __syncthreads();
         {
             // S = V^T X
@@ -308,7 +401,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            for (int ch = wid; ch < nch; ch += TS_WARPS) {
+            for (int ch = wid; ch < nch; ch += WARPS) {
                 const int r0 = m0 + 32 * ch;
                 double fv[4][8], fx[4][8];
 #pragma unroll
@@ -334,7 +427,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         }
         __syncthreads();
         // M1 = S T
-        for (int t = tid; t < 1024; t += TS_THREADS) {
+        for (int t = tid; t < 1024; t += NT) {
             const int row = t >> 5, col = t & 31;
             double s = 0.0;
             for (int l = 0; l <= col; ++l) s += G[row][l] * Ts[l][col];
@@ -342,7 +435,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         }
         __syncthreads();
         // M2 = T^T M1 -> G
-        for (int t = tid; t < 1024; t += TS_THREADS) {
+        for (int t = tid; t < 1024; t += NT) {
             const int row = t >> 5, col = t & 31;
             double s = 0.0;
             for (int l = 0; l <= row; ++l) s += Ts[l][row] * M1[l][col];
@@ -350,13 +443,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         }
         __syncthreads();
         // operand tiles [n][k]: T and -M2/2
-        for (int t = tid; t < 1024; t += TS_THREADS) {
+        for (int t = tid; t < 1024; t += NT) {
             const int n = t >> 5, k = t & 31;
             Bs[0][0][n][k] = Ts[k][n];
             Bs[0][1][n][k] = -0.5 * G[k][n];
         }
         __syncthreads();
-        for (int ch = wid; ch < nch; ch += TS_WARPS) {
+        for (int ch = wid; ch < nch; ch += WARPS) {
             const int r0 = m0 + 32 * ch;
             double fx[4][8], fv[4][8];
 #pragma unroll
@@ -396,58 +489,79 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         TSP(4)
 
         // ---------------------------------------------------------------- A22 -= V W^T + W V^T
-        auto stageWV = [&](int buf, int J) {
-            const int k = tid >> 5, n = tid & 31;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-                Bs[buf][0][n][k + 8 * i4] = Wp[(size_t)(k + 8 * i4) * np + 32 * J + n];
-                Bs[buf][1][n][k + 8 * i4] = Vp[(size_t)(k + 8 * i4) * np + 32 * J + n];
-            }
-        };
-        stageWV(0, Jt);
-        __syncthreads();
-        for (int J = Jt; J < NB; ++J) {
-            const int buf = (J - Jt) & 1;
-            if (J + 1 < NB) stageWV(buf ^ 1, J + 1);
-            for (int I = J + ((wid - (J & 7) + 8) & 7); I < NB; I += TS_WARPS) {
-                const int ar0 = 32 * I + grp;
-                double *cp0 = &A[ar0 + (size_t)(32 * J + 2 * tig) * lda];
-                double c0[4][4], c1[4][4];
+        // warp <-> block row I (groups of WARPS): the A-operand fragments -V_I, -W_I stay in
+        // registers for the whole sweep over J <= I; W_J, V_J are shared through shared memory;
+        // the next C tile arrives in the transit tile by cp.async during the 256 DMMAs.
+        for (int g0 = Jt; g0 < NB; g0 += WARPS) {
+            const int I = g0 + wid;
+            const bool act = I < NB;
+            const int Jmax = min(g0 + WARPS - 1, NB - 1);
+            double fv[4][8], fw[4][8];
+            if (act) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        c0[x][y] = __ldcg(cp0 + 8 * x + (size_t)(8 * y) * lda);
-                        c1[x][y] = __ldcg(cp0 + 8 * x + (size_t)(8 * y + 1) * lda);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        fv[x][ks] = -Vp[(size_t)(4 * ks + tig) * np + 32 * I + 8 * x + grp];
+                        fw[x][ks] = -Wp[(size_t)(4 * ks + tig) * np + 32 * I + 8 * x + grp];
                     }
+            }
+            auto fillWV = [&](int buf, int J) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    double fv[4], fw[4];
+                for (int n = 0; n < SV; ++n) {
+                    cp_async8_t(&Bs[buf][0][lane][wid + WARPS * n], &Wp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
+                    cp_async8_t(&Bs[buf][1][lane][wid + WARPS * n], &Vp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
+                }
+            };
+            __syncthreads();
+            if (act) issue_tile(I, Jt);
+            fillWV(0, Jt);
+            cp_async_wait_all_t();
+            __syncthreads();
+            for (int J = Jt; J <= Jmax; ++J) {
+                const int buf = (J - Jt) & 1;
+                const bool work = act && J <= I;
+                double c0[4][4], c1[4][4];
+                if (work) {
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        fv[x] = -Vp[(size_t)(4 * ks + tig) * np + ar0 + 8 * x];
-                        fw[x] = -Wp[(size_t)(4 * ks + tig) * np + ar0 + 8 * x];
-                    }
+                    for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
-                        const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
+                        for (int y = 0; y < 4; ++y) {
+                            c0[x][y] = Tw[(8 * y + 2 * tig) * TSTR + 8 * x + grp];
+                            c1[x][y] = Tw[(8 * y + 2 * tig + 1) * TSTR + 8 * x + grp];
+                        }
+                }
+                __syncwarp();
+                if (J + 1 <= Jmax) {
+                    if (act && J + 1 <= I) issue_tile(I, J + 1);
+                    fillWV(buf ^ 1, J + 1);
+                }
+                if (work) {
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
-                            dmma_t(c0[x][y], c1[x][y], fw[x], bv);
+                    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
+                            const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                dmma_t(c0[x][y], c1[x][y], fv[x][ks], bw);
+                                dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
+                            }
                         }
                     }
+                    double *cp0 = &A[32 * I + grp + (size_t)(32 * J + 2 * tig) * lda];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            cp0[8 * x + (size_t)(8 * y) * lda] = c0[x][y];
+                            cp0[8 * x + (size_t)(8 * y + 1) * lda] = c1[x][y];
+                        }
                 }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        cp0[8 * x + (size_t)(8 * y) * lda] = c0[x][y];
-                        cp0[8 * x + (size_t)(8 * y + 1) * lda] = c1[x][y];
-                    }
+                cp_async_wait_all_t();
+                __syncthreads();
             }
-            __syncthreads();
         }
         TSP(5)
     }  // panels
@@ -463,7 +577,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sy2sb_kernel(TsArgs a)
         double *__restrict__ Bd = slot + a.oBand;
         const int N = a.N;
         const int total = EIG_LDB * (np + 64);
-        for (int idx = tid; idx < total; idx += TS_THREADS) {
+        for (int idx = tid; idx < total; idx += NT) {
             const int d = idx % EIG_LDB, j = idx / EIG_LDB;
             double x = 0.0;
             if (d <= 32 && j + d < N) x = A[(j + d) + (size_t)j * lda];
@@ -666,29 +780,64 @@ __global__ void __launch_bounds__(256) zt_out_kernel(TsArgs a)
     }
 }
 
-// grid (ceil(nslabs / 8), nmat); warp <-> slab of 32 eigenvector columns, lane <-> column
-__global__ void __launch_bounds__(TS_THREADS) q2_kernel(TsArgs a)
+// grid (ceil(nslabs / 8), nmat); warp <-> slab of 32 eigenvector columns, lane <-> column.
+// The 8 warps of a CTA walk the same (group, step) sequence of one matrix: the 32 reflectors of
+// the next block (8 KB) and their taus are prefetched into registers while the current block is
+// applied from shared memory (broadcast reads), one __syncthreads per block.
+constexpr int Q2_WARPS = 4;
+__global__ void __launch_bounds__(Q2_WARPS * 32, 2) q2_kernel(TsArgs a)
 {
+    __shared__ __align__(16) double Vs[2][32][32];
+    __shared__ double taus[2][32];
     const int mat = blockIdx.y;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slab = blockIdx.x * TS_WARPS + wid;
-    if (slab * 32 >= a.kp) return;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int slab = blockIdx.x * Q2_WARPS + wid;
+    const bool act = slab * 32 < a.kp;
     double *slot = a.base + (size_t)mat * a.slot;
     const double *__restrict__ V2 = slot + a.oV2;
     const double *__restrict__ tau2 = slot + a.oTau2;
-    double *Zc = slot + a.oZt + slab * 32 + lane;
+    double *Zc = slot + a.oZt + (act ? slab * 32 + lane : 0);
     const int N = a.N, ldv = a.Npad, TM = a.NB + 2;
     const size_t kp = (size_t)a.kp;
     const int nsw = N - 2;
     const int ngroups = (nsw + 31) / 32;
-    for (int G = ngroups - 1; G >= 0; --G) {
+    if (ngroups <= 0) return;
+
+    auto fetch = [&](int G, int t, double(&pv)[32 / Q2_WARPS], double &pt) {
         const int s0 = 32 * G;
-        for (int t = 0; s0 + 1 + 32 * t < N; ++t) {
+#pragma unroll
+        for (int i = 0; i < 32 / Q2_WARPS; ++i) {
+            const int s = s0 + wid + Q2_WARPS * i, row = s + 1 + 32 * t + lane;
+            pv[i] = (s < nsw && row < N) ? V2[(size_t)s * ldv + row] : 0.0;
+        }
+        pt = 0.0;
+        if (tid < 32) {
+            const int s = s0 + tid;
+            if (s < nsw && s + 1 + 32 * t < N) pt = tau2[(size_t)s * TM + t];
+        }
+    };
+    auto stash = [&](int buf, const double(&pv)[32 / Q2_WARPS], double pt) {
+#pragma unroll
+        for (int i = 0; i < 32 / Q2_WARPS; ++i) Vs[buf][wid + Q2_WARPS * i][lane] = pv[i];
+        if (tid < 32) taus[buf][tid] = pt;
+    };
+
+    int G = ngroups - 1, t = 0, buf = 0;
+    double pv[32 / Q2_WARPS], pt;
+    fetch(G, t, pv, pt);
+    stash(0, pv, pt);
+    __syncthreads();
+    while (true) {
+        int Gn = G, tn = t + 1;
+        if (32 * Gn + 1 + 32 * tn >= N) { Gn = G - 1; tn = 0; }
+        const bool more = Gn >= 0;
+        if (more) fetch(Gn, tn, pv, pt);
+        if (act) {
+            const int s0 = 32 * G;
             double zr[39];
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
-                const int s_hi = s0 + 31 - 8 * sub;
-                const int Rb = s_hi - 6 + 32 * t;
+                const int Rb = s0 + 31 - 8 * sub - 6 + 32 * t;
                 if (sub == 0) {
 #pragma unroll
                     for (int x = 0; x < 39; ++x) zr[x] = Zc[(size_t)(Rb + x) * kp];
@@ -700,26 +849,25 @@ __global__ void __launch_bounds__(TS_THREADS) q2_kernel(TsArgs a)
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int s = s_hi - u;
-                    if (s < nsw) {
-                        const double tau = tau2[(size_t)s * TM + t];
-                        if (tau != 0.0) {
-                            const int r = s + 1 + 32 * t;
-                            const double *vp = V2 + (size_t)s * ldv + r;
-                            double vl[32];
+                    const int sw = 31 - 8 * sub - u;
+                    const double tau = taus[buf][sw];
+                    if (tau != 0.0) {
+                        const double2 *vv = reinterpret_cast<const double2 *>(&Vs[buf][sw][0]);
+                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                            for (int l = 0; l < 32; ++l) vl[l] = (r + l < N) ? __ldg(vp + l) : 0.0;
-                            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                        for (int l2 = 0; l2 < 16; l2 += 2) {
+                            const double2 x0 = vv[l2], x1 = vv[l2 + 1];
+                            d0 += x0.x * zr[7 - u + 2 * l2];
+                            d1 += x0.y * zr[7 - u + 2 * l2 + 1];
+                            d2 += x1.x * zr[7 - u + 2 * l2 + 2];
+                            d3 += x1.y * zr[7 - u + 2 * l2 + 3];
+                        }
+                        const double dot = tau * ((d0 + d1) + (d2 + d3));
 #pragma unroll
-                            for (int l = 0; l < 32; l += 4) {
-                                d0 += vl[l] * zr[7 - u + l];
-                                d1 += vl[l + 1] * zr[7 - u + l + 1];
-                                d2 += vl[l + 2] * zr[7 - u + l + 2];
-                                d3 += vl[l + 3] * zr[7 - u + l + 3];
-                            }
-                            const double dot = tau * ((d0 + d1) + (d2 + d3));
-#pragma unroll
-                            for (int l = 0; l < 32; ++l) zr[7 - u + l] -= dot * vl[l];
+                        for (int l2 = 0; l2 < 16; ++l2) {
+                            const double2 x0 = vv[l2];
+                            zr[7 - u + 2 * l2] -= dot * x0.x;
+                            zr[7 - u + 2 * l2 + 1] -= dot * x0.y;
                         }
                     }
                 }
@@ -732,6 +880,10 @@ __global__ void __launch_bounds__(TS_THREADS) q2_kernel(TsArgs a)
                 }
             }
         }
+        if (more) stash(buf ^ 1, pv, pt);
+        __syncthreads();
+        if (!more) break;
+        G = Gn; t = tn; buf ^= 1;
     }
 }
 
@@ -761,9 +913,17 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 {
     if (!S.L.two_stage) { arcb200_set_error("sy2sb: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
-    const size_t smem = (8448 + 3 * 1056 + 512 + 64) * sizeof(double);
-    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<<<nmat, TS_THREADS, smem, st>>>(a);
+    const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
+    const int warps = ev ? atoi(ev) : (nmat > 148 ? 4 : 8);
+    if (warps == 4) {
+        const size_t smem = (4 * 32 * 40 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sy2sb_kernel<4><<<nmat, 128, smem, st>>>(a);
+    } else {
+        const size_t smem = (8 * 32 * 40 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sy2sb_kernel<8><<<nmat, 256, smem, st>>>(a);
+    }
     ARCB200_LAUNCH_CHECK("sy2sb_kernel");
     if (launches) *launches += 1;
     return 0;
@@ -792,7 +952,7 @@ int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, c
     const int rowtiles = (S.L.Npad + 64) / 32, coltiles = a.kp / 32;
     zt_in_kernel<<<dim3(rowtiles, coltiles, nmat), 256, 0, st>>>(a);
     const int nslab = a.kp / 32;
-    q2_kernel<<<dim3((nslab + TS_WARPS - 1) / TS_WARPS, nmat), TS_THREADS, 0, st>>>(a);
+    q2_kernel<<<dim3((nslab + Q2_WARPS - 1) / Q2_WARPS, nmat), Q2_WARPS * 32, 0, st>>>(a);
     zt_out_kernel<<<dim3(S.L.NB, coltiles, nmat), 256, 0, st>>>(a);
     ARCB200_LAUNCH_CHECK("q2 kernels");
     if (launches) *launches += 3;
