@@ -81,7 +81,8 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
 {
     constexpr int NT = WARPS * 32;
-    constexpr int TSTR = 40;                         // per-warp transit tile [cc][TSTR] (column-major)
+    constexpr int TSTR = 36;                         // per-warp transit tile [cc][TSTR] (column-major):
+                                                     // conflict-free LDS.64 fragments in both orientations
     constexpr int UNI = WARPS * 32 * TSTR + 4608;    // transit tiles + operand tiles (doubles)
     const int mat = blockIdx.x;
     const int np = a.Npad, lda = a.Npad, NB = a.NB;
@@ -339,24 +340,20 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                 const int buf = (q - Jt) & 1;
                 double fa[4][8];
                 if (act) {
-                    if (q < i) {
+                    // diagonal tiles are kept fully symmetric (both triangles are updated), so
+                    // q == i reads like a stored tile
+                    if (q <= i) {
+                        const double *pd = Tw + tig * TSTR + grp;
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = Tw[(4 * ks + tig) * TSTR + 8 * x + grp];
-                    } else if (q > i) {
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = Tw[(8 * x + grp) * TSTR + 4 * ks + tig];
+                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = pd[4 * ks * TSTR + 8 * x];
                     } else {
+                        const double *pt = Tw + grp * TSTR + tig;
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) {
-                                const int rr = 8 * x + grp, cc = 4 * ks + tig;
-                                fa[x][ks] = (rr >= cc) ? Tw[cc * TSTR + rr] : Tw[rr * TSTR + cc];
-                            }
+                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = pt[8 * x * TSTR + 4 * ks];
                     }
                 }
                 __syncwarp();
@@ -492,6 +489,8 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
         // warp <-> block row I (groups of WARPS): the A-operand fragments -V_I, -W_I stay in
         // registers for the whole sweep over J <= I; W_J, V_J are shared through shared memory;
         // the next C tile arrives in the transit tile by cp.async during the 256 DMMAs.
+        // Fragment row mapping here: DMMA row (x, grp) <-> tile row 4 grp + x, so that a lane's
+        // four rows are contiguous (128-bit shared loads and global stores).
         for (int g0 = Jt; g0 < NB; g0 += WARPS) {
             const int I = g0 + wid;
             const bool act = I < NB;
@@ -499,12 +498,13 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
             double fv[4][8], fw[4][8];
             if (act) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        fv[x][ks] = -Vp[(size_t)(4 * ks + tig) * np + 32 * I + 8 * x + grp];
-                        fw[x][ks] = -Wp[(size_t)(4 * ks + tig) * np + 32 * I + 8 * x + grp];
-                    }
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double2 *pv2 = reinterpret_cast<const double2 *>(Vp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                    const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                    const double2 v0 = pv2[0], v1 = pv2[1], w0 = pw2[0], w1 = pw2[1];
+                    fv[0][ks] = -v0.x; fv[1][ks] = -v0.y; fv[2][ks] = -v1.x; fv[3][ks] = -v1.y;
+                    fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
+                }
             }
             auto fillWV = [&](int buf, int J) {
 #pragma unroll
@@ -518,18 +518,20 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
             fillWV(0, Jt);
             cp_async_wait_all_t();
             __syncthreads();
+            const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
             for (int J = Jt; J <= Jmax; ++J) {
                 const int buf = (J - Jt) & 1;
                 const bool work = act && J <= I;
-                double c0[4][4], c1[4][4];
+                double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
                 if (work) {
 #pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            c0[x][y] = Tw[(8 * y + 2 * tig) * TSTR + 8 * x + grp];
-                            c1[x][y] = Tw[(8 * y + 2 * tig + 1) * TSTR + 8 * x + grp];
-                        }
+                    for (int y = 0; y < 4; ++y) {
+                        const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
+                        const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
+                        const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                        c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
+                        c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
+                    }
                 }
                 __syncwarp();
                 if (J + 1 <= Jmax) {
@@ -550,14 +552,16 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                             }
                         }
                     }
-                    double *cp0 = &A[32 * I + grp + (size_t)(32 * J + 2 * tig) * lda];
+                    double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            cp0[8 * x + (size_t)(8 * y) * lda] = c0[x][y];
-                            cp0[8 * x + (size_t)(8 * y + 1) * lda] = c1[x][y];
-                        }
+                    for (int y = 0; y < 4; ++y) {
+                        double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
+                        double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
+                        o0[0] = make_double2(c0[0][y], c0[1][y]);
+                        o0[1] = make_double2(c0[2][y], c0[3][y]);
+                        o1[0] = make_double2(c1[0][y], c1[1][y]);
+                        o1[1] = make_double2(c1[2][y], c1[3][y]);
+                    }
                 }
                 cp_async_wait_all_t();
                 __syncthreads();
@@ -622,6 +626,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
     double *vs = sm + TS_WARPS * 32 * 33 + wid * 32;
     double *ws = sm + TS_WARPS * 32 * 33 + TS_WARPS * 32 + wid * 32;
     __shared__ volatile int prog[64];
+    TSP_DECL
     if (tid < 64) prog[tid] = -1;
     for (size_t i = tid; i < (size_t)a.Npad * TM; i += TS_THREADS) tau2[i] = 0.0;
     __syncthreads();
@@ -638,7 +643,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
             }
         };
         int t = 0;
+        TSP(0)
         wait_for(0);
+        TSP(1)
         int r = s + 1;
         int L = min(32, N - r);
         double v, tau, beta;
@@ -663,19 +670,34 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
             }
             vs[lane] = v;
             __syncwarp();
+#ifdef TS_PROFILE
+            if (Dl[0] + El[0] == 1.2345e300) tsp_t[7]++;      // force the loads to complete here
+#endif
+            TSP(2)
             if (tau != 0.0) {
                 // D <- H D H on the lower triangle
-                double pd = 0.0;
+                // four partial sums per reduction: the dependent FP64 chains are the critical path
+                double pd0 = 0.0, pd1 = 0.0, pd2 = 0.0, pd3 = 0.0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pd += Dl[j] * vs[j];
+                for (int j = 0; j < 32; j += 4) {
+                    pd0 += Dl[j] * vs[j];
+                    pd1 += Dl[j + 1] * vs[j + 1];
+                    pd2 += Dl[j + 2] * vs[j + 2];
+                    pd3 += Dl[j + 3] * vs[j + 3];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = (j < lane) ? Dl[j] * v : 0.0;
                 __syncwarp();
-                double pt = 0.0;
+                double pt0 = 0.0, pt1 = 0.0, pt2 = 0.0, pt3 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) pt += tile[i * 33 + lane];
+                for (int i = 0; i < 32; i += 4) {
+                    pt0 += tile[i * 33 + lane];
+                    pt1 += tile[(i + 1) * 33 + lane];
+                    pt2 += tile[(i + 2) * 33 + lane];
+                    pt3 += tile[(i + 3) * 33 + lane];
+                }
                 __syncwarp();
-                const double pv = tau * (pd + pt);
+                const double pv = tau * (((pd0 + pd1) + (pd2 + pd3)) + ((pt0 + pt1) + (pt2 + pt3)));
                 const double al = 0.5 * tau * warp_sum(pv * v);
                 const double w = pv - al * v;
                 ws[lane] = w;
@@ -689,13 +711,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
                 }
                 __syncwarp();
             }
+            TSP(3)
             if (L2 <= 0) break;
             // E <- E H
             if (tau != 0.0) {
-                double y = 0.0;
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) y += El[j] * vs[j];
-                y *= tau;
+                for (int j = 0; j < 32; j += 4) {
+                    y0 += El[j] * vs[j];
+                    y1 += El[j + 1] * vs[j + 1];
+                    y2 += El[j + 2] * vs[j + 2];
+                    y3 += El[j + 3] * vs[j + 3];
+                }
+                const double y = tau * ((y0 + y1) + (y2 + y3));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) El[j] -= y * vs[j];
             }
@@ -707,9 +735,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v2 * El[j];
                 __syncwarp();
-                double sj = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sj += tile[i * 33 + lane];
+                for (int i = 0; i < 32; i += 4) {
+                    s0 += tile[i * 33 + lane];
+                    s1 += tile[(i + 1) * 33 + lane];
+                    s2 += tile[(i + 2) * 33 + lane];
+                    s3 += tile[(i + 3) * 33 + lane];
+                }
+                const double sj = (s0 + s1) + (s2 + s3);
                 __syncwarp();
                 ws[lane] = (lane == 0) ? 0.0 : sj * tau_n;
                 __syncwarp();
@@ -721,19 +755,27 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
                 for (int j = 0; j < 32; ++j) BD(r2 + lane, r + j) = El[j];
             }
             __syncwarp();
+            TSP(4)
             r = r2; L = L2; v = v2; tau = tau_n;
             ++t;
             __threadfence_block();
             __syncwarp();
             __threadfence_block();
             if (lane == 0) prog[s & 63] = s * 4096 + t;
+            TSP(5)
             wait_for(t);
+            TSP(1)
         }
         __threadfence_block();
         __syncwarp();
         __threadfence_block();
         if (lane == 0) prog[s & 63] = s * 4096 + 4095;
     }
+#ifdef TS_PROFILE
+    if (mat == 0 && lane == 0 && (wid == 0 || wid == 5))
+        printf("sb2st prof warp %d (10 kcycles): wait %lld loads %lld D %lld E %lld publish %lld other %lld\n", wid,
+               tsp_t[1] / 10000, tsp_t[2] / 10000, tsp_t[3] / 10000, tsp_t[4] / 10000, tsp_t[5] / 10000, tsp_t[0] / 10000);
+#endif
     __syncthreads();
     for (int i = tid; i < N; i += TS_THREADS) {
         dd[i] = Bd[(size_t)i * EIG_LDB];
@@ -916,11 +958,11 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
     const int warps = ev ? atoi(ev) : (nmat > 148 ? 4 : 8);
     if (warps == 4) {
-        const size_t smem = (4 * 32 * 40 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
+        const size_t smem = (4 * 32 * 36 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<4><<<nmat, 128, smem, st>>>(a);
     } else {
-        const size_t smem = (8 * 32 * 40 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
+        const size_t smem = (8 * 32 * 36 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<8><<<nmat, 256, smem, st>>>(a);
     }

@@ -41,6 +41,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def peaks_raw():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -192,7 +200,7 @@ def bench_c3(args, rank, world):
         sw.dist_info = old
     e2e_value = npts * world * args.steps / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel (sytrd_kernel): time it alone on one batch
+    # roofline of the dominant kernel: time it alone on one batch
     hbm, hbm_src = measured_peaks()
     batch = sweep._pick_batch(N, npts, k, torch.cuda.current_device())
     rng = np.random.default_rng(0)
@@ -206,30 +214,65 @@ def bench_c3(args, rank, world):
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     del A
+    two_stage = os.environ.get("ARCB200_TWO_STAGE", "1") != "0" and 1024 <= N <= 4096
 
-    def sy():
-        rc = lib.arcb200_sytrd_batched(dev.index, _lib.stream_ptr(dev.index), N, nb, _lib.ptr(d_A),
-                                       _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
-                                       _lib.ptr(work), wbytes, 0)
-        _lib.check(rc, "sytrd")
-    # the entry point = load kernel + sytrd kernel + 3 tiny copies; subtract the load pass
-    for _ in range(2):
-        sy()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        sy()
-    e1.record()
-    torch.cuda.synchronize()
-    sy_ms = e0.elapsed_time(e1) / 3
-    alg_bytes = (4.0 / 3.0) * float(N) ** 3 * nb          # (4/3) N^3 bytes per solve
-    achieved = alg_bytes / (sy_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "sytrd_kernel (blocked Householder tridiagonalisation, symv sweeps)",
-            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": load_traffic("sytrd_c3"), "peak_source": hbm_src,
-            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sy_ms, "matrices_per_launch": nb,
-            "note": "timed via arcb200_sytrd_batched (includes one N^2 load pass per matrix)"}
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    if two_stage:
+        # sy2sb_kernel (dense -> band, DMMA): (4/3) N^3 flop per matrix, tensor bound.  The
+        # entry point = load pass + sy2sb kernel + band copy (two N^2 passes, < 1 % of the time).
+        band = torch.zeros((nb, N, 33), dtype=torch.float64, device=dev)
+
+        def sy():
+            rc = lib.arcb200_sy2sb_batched(dev.index, _lib.stream_ptr(dev.index), N, nb, _lib.ptr(d_A),
+                                           _lib.ptr(band), _lib.ptr(work), wbytes)
+            _lib.check(rc, "sy2sb")
+        sy_ms = timed(sy)
+        scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+        import ctypes
+        tf = ctypes.c_double(0.0)
+        _lib.check(lib.arcb200_dmma_peak(dev.index, _lib.stream_ptr(dev.index), _lib.ptr(scratch),
+                                         ctypes.addressof(tf)), "dmma_peak")
+        flops = (4.0 / 3.0) * float(N) ** 3 * nb
+        achieved = flops / (sy_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "sy2sb_kernel (dense -> band reduction: panel QR + symmetric product "
+                "+ rank-2k update on FP64 tensor cores, mma.sync.m8n8k4.f64)",
+                "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
+                "traffic": load_traffic("sy2sb_c3"),
+                "peak_source": "measured in this run: register-only mma.sync.m8n8k4.f64 loop, 8 warps/SM "
+                               "(arcb200_dmma_peak); MEASURED_PEAKS.json has no FP64 figure (bf16 %s TFLOP/s, HBM %s GB/s)"
+                               % (peaks_raw().get("bf16_tflops"), hbm),
+                "algorithmic_flop_per_launch": flops, "launch_ms": sy_ms, "matrices_per_launch": nb,
+                "hbm_view": {"algorithmic_bytes_per_launch": float(N) ** 3 / 6.0 * nb,
+                             "achieved_gbs": float(N) ** 3 / 6.0 * nb / (sy_ms * 1e-3) / 1e9, "peak_gbs": hbm,
+                             "note": "two reads of the trailing lower triangle (symmetric product) + one "
+                                     "read-modify-write (rank-2k update) per 32-column panel = N^3/6 bytes"},
+                "note": "timed via arcb200_sy2sb_batched (includes one N^2 load pass and the band copy)"}
+        del band
+    else:
+        def sy():
+            rc = lib.arcb200_sytrd_batched(dev.index, _lib.stream_ptr(dev.index), N, nb, _lib.ptr(d_A),
+                                           _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
+                                           _lib.ptr(work), wbytes, 0)
+            _lib.check(rc, "sytrd")
+        sy_ms = timed(sy)
+        alg_bytes = (4.0 / 3.0) * float(N) ** 3 * nb          # (4/3) N^3 bytes per solve
+        achieved = alg_bytes / (sy_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "sytrd_kernel (blocked Householder tridiagonalisation, symv sweeps)",
+                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": load_traffic("sytrd_c3"), "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sy_ms, "matrices_per_launch": nb,
+                "note": "timed via arcb200_sytrd_batched (includes one N^2 load pass per matrix)"}
     del d_A, work
     out = {"value": value, "ms": ms, "e2e_value": e2e_value, "ms_e2e": ms_e2e, "h2d": h2d, "d2h": d2h,
            "launches": launches[0], "roofline": roof, "clocks": clk.summary(), "N": N, "k": k,

@@ -34,6 +34,11 @@ const char *arcb200_last_error(void);
  *                      total_mem_MiB, cluster_launch_supported, clock_khz} */
 int arcb200_device_info(int device, int64_t *props);
 
+/* FP64 tensor-core (mma.sync.m8n8k4.f64) peak of the device in TFLOP/s, register operands
+ * only: the denominator of the roofline of the DMMA-bound eigensolver kernels (the driver's
+ * MEASURED_PEAKS.json has no FP64 figure).  d_scratch: one device double. */
+int arcb200_dmma_peak(int device, void *stream, double *d_scratch, double *h_tflops);
+
 /* ------------------------------------------------------------------------ */
 /* subsystem (1): Numerov radial wavefunctions + radial integrals            */
 /* ------------------------------------------------------------------------ */
