@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
     constexpr int NT = WARPS * 32;
     constexpr int TSTR = 36;                         // per-warp transit tile [cc][TSTR] (column-major):
                                                      // conflict-free LDS.64 fragments in both orientations
-    constexpr int UNI = WARPS * 32 * TSTR + 4608;    // transit tiles + operand tiles (doubles)
+    constexpr int UNI = 2 * WARPS * 32 * TSTR + 4608;   // 2 transit tiles per warp + operand tiles (doubles)
     const int mat = blockIdx.x;
     const int np = a.Npad, lda = a.Npad, NB = a.NB;
     double *slot = a.base + (size_t)mat * a.slot;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
 
     extern __shared__ double sm[];
     double *uni = sm;
-    double(*Bs)[2][32][BSTR] = reinterpret_cast<double(*)[2][32][BSTR]>(uni + WARPS * 32 * TSTR);   // [buf][op][n][k]
+    double(*Bs)[2][32][BSTR] = reinterpret_cast<double(*)[2][32][BSTR]>(uni + 2 * WARPS * 32 * TSTR);   // [buf][op][n][k]
     double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + UNI);
     double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
     double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
@@ -107,15 +107,20 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int grp = lane >> 2, tig = lane & 3;
-    double *Tw = uni + wid * (32 * TSTR);
+    double *Tw = uni + wid * (2 * 32 * TSTR);          // two transit tiles per warp
     // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
     // tile: 16-byte pieces, whole 256-byte column segments per half warp
-    auto issue_tile = [&](int Ib, int Jb) {
-        const double *src = A + (size_t)(32 * Jb) * lda + 32 * Ib;
-#pragma unroll
+    auto issue_tile = [&](int Ib, int Jb, int tb) {
+        // a real loop with running pointers: sixteen hoisted 64-bit addresses would cost 48
+        // registers in the middle of the tensor-core loops
+        const double *src = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+        double *dst = Tw + tb * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+        const size_t sstep = 2 * (size_t)lda;
+#pragma unroll 1
         for (int k = 0; k < 16; ++k) {
-            const int pi = lane + 32 * k, cc = pi >> 4, ro = (pi & 15) * 2;
-            cp_async16_t(&Tw[cc * TSTR + ro], src + (size_t)cc * lda + ro);
+            cp_async16_t(dst, src);
+            src += sstep;
+            dst += 2 * TSTR;
         }
     };
 
@@ -199,34 +204,48 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                 double g[KO], h[KO];
 #pragma unroll
                 for (int k = 0; k < KO; ++k) g[k] = h[k] = 0.0;
-                double va[4], xa[4], oa[4][KO], vb[4], xb[4], ob[4][KO];
-                auto loadB = [&](int b, double(&vv)[4], double(&xx)[4], double(&oo)[4][KO]) {
+                // the warp streams (column c, column cn, own columns) x all rows through a ring of
+                // chunk slots in its transit-tile area with cp.async, RD chunks ahead: the pass is
+                // no longer a chain of exposed DRAM round trips.  lane <-> row for the copy and
+                // for the arithmetic, so only the thread's own copies have to be waited for.
+                {
+                    constexpr int SLOTW = (2 + KO) * 32;
+                    constexpr int NSLOT = (2 * 32 * TSTR) / SLOTW;
+                    constexpr int RD = (NSLOT - 2 < 8) ? NSLOT - 2 : 8;
+                    double *ring = Tw;
+                    auto issueB = [&](int ch) {
+                        if (ch < nch) {
+                            const int r = m0 + 32 * ch + lane;
+                            double *dst = ring + (ch % NSLOT) * SLOTW + lane;
+                            if (c >= 0) cp_async8_t(dst, Vp + (size_t)c * np + r);
+                            cp_async8_t(dst + 32, P + r + (size_t)cn * lda);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ch = 4 * b + u, r = m0 + 32 * ch + lane;
-                        const bool ok = ch < nch;
-                        vv[u] = (ok && c >= 0) ? Vp[(size_t)c * np + r] : 0.0;
-                        xx[u] = ok ? P[r + (size_t)cn * lda] : 0.0;
-#pragma unroll
-                        for (int k = 0; k < KO; ++k) {
-                            const int j = wid + WARPS * k;
-                            oo[u][k] = (ok && j > cn) ? P[r + (size_t)j * lda] : 0.0;
+                            for (int k = 0; k < KO; ++k) {
+                                const int j = wid + WARPS * k;
+                                if (j > cn) cp_async8_t(dst + 64 + 32 * k, P + r + (size_t)j * lda);
+                            }
                         }
-                    }
-                };
-                auto compB = [&](int b, const double(&vv)[4], const double(&xx)[4], const double(&oo)[4][KO]) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ch = 4 * b + u, r = m0 + 32 * ch + lane;
-                        if (ch < nch && r >= rd) {
-                            const double xg = (r > rd + 1) ? xx[u] : 0.0;
+                        asm volatile("cp.async.commit_group;\n" ::: "memory");
+                    };
+#pragma unroll 1
+                    for (int ch = 0; ch < RD; ++ch) issueB(ch);
+#pragma unroll 1
+                    for (int ch = 0; ch < nch; ++ch) {
+                        issueB(ch + RD);
+                        asm volatile("cp.async.wait_group %0;\n" ::"n"(RD) : "memory");
+                        const int r = m0 + 32 * ch + lane;
+                        if (r >= rd) {
+                            const double *sl = ring + (ch % NSLOT) * SLOTW + lane;
+                            const double v = (c >= 0) ? sl[0] : 0.0;
+                            const double xc = sl[32];
+                            const double xg = (r > rd + 1) ? xc : 0.0;
 #pragma unroll
                             for (int k = 0; k < KO; ++k) {
                                 const int j = wid + WARPS * k;
                                 if (j > cn) {
-                                    double x = oo[u][k];
+                                    double x = sl[64 + 32 * k];
                                     if (c >= 0) {
-                                        x -= vv[u] * wreg[k];
+                                        x -= v * wreg[k];
                                         P[r + (size_t)j * lda] = x;
                                     }
                                     g[k] += xg * x;
@@ -235,16 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                             }
                         }
                     }
-                };
-                const int nbat = (nch + 3) / 4;
-                loadB(0, va, xa, oa);
-                for (int b = 0; b < nbat; b += 2) {
-                    if (b + 1 < nbat) loadB(b + 1, vb, xb, ob);
-                    compB(b, va, xa, oa);
-                    if (b + 1 < nbat) {
-                        if (b + 2 < nbat) loadB(b + 2, va, xa, oa);
-                        compB(b + 1, vb, xb, ob);
-                    }
+                    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
                 }
 #pragma unroll
                 for (int k = 0; k < KO; ++k) {
@@ -332,43 +342,48 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                     cp_async8_t(&Bs[buf][0][wid + WARPS * n][lane], &Vp[(size_t)(wid + WARPS * n) * np + 32 * q + lane]);
             };
             __syncthreads();
-            if (act) issue_tile(max(i, Jt), min(i, Jt));
+            if (act) issue_tile(max(i, Jt), min(i, Jt), 0);
             fillV(0, Jt);
             cp_async_wait_all_t();
             __syncthreads();
             for (int q = Jt; q < NB; ++q) {
                 const int buf = (q - Jt) & 1;
-                double fa[4][8];
-                if (act) {
-                    // diagonal tiles are kept fully symmetric (both triangles are updated), so
-                    // q == i reads like a stored tile
-                    if (q <= i) {
-                        const double *pd = Tw + tig * TSTR + grp;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = pd[4 * ks * TSTR + 8 * x];
-                    } else {
-                        const double *pt = Tw + grp * TSTR + tig;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) fa[x][ks] = pt[8 * x * TSTR + 4 * ks];
-                    }
-                }
-                __syncwarp();
                 if (q + 1 < NB) {
-                    if (act) issue_tile(max(i, q + 1), min(i, q + 1));
+                    if (act) issue_tile(max(i, q + 1), min(i, q + 1), buf ^ 1);
                     fillV(buf ^ 1, q + 1);
                 }
                 if (act) {
+                    // fragments straight from the transit tile inside the k loop (no register
+                    // array); diagonal tiles are kept fully symmetric, so q == i reads like a
+                    // stored tile
+                    const double *tw = Tw + buf * (32 * TSTR);
+                    if (q <= i) {
+                        const double *pd = tw + tig * TSTR + grp;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
+                        for (int ks = 0; ks < 8; ++ks) {
+                            double fa[4];
 #pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
+                            for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
 #pragma unroll
-                            for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x][ks], b);
+                            for (int y = 0; y < 4; ++y) {
+                                const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                            }
+                        }
+                    } else {
+                        const double *pt = tw + grp * TSTR + tig;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            double fa[4];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) {
+                                const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                            }
                         }
                     }
                 }
@@ -495,17 +510,17 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
             const int I = g0 + wid;
             const bool act = I < NB;
             const int Jmax = min(g0 + WARPS - 1, NB - 1);
-            double fv[4][8], fw[4][8];
+            // -W_I in registers; -V_I in the warp's second transit tile ([k][row], pitch TSTR)
+            double fw[4][8];
             if (act) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const double2 *pv2 = reinterpret_cast<const double2 *>(Vp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
                     const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
-                    const double2 v0 = pv2[0], v1 = pv2[1], w0 = pw2[0], w1 = pw2[1];
-                    fv[0][ks] = -v0.x; fv[1][ks] = -v0.y; fv[2][ks] = -v1.x; fv[3][ks] = -v1.y;
+                    const double2 w0 = pw2[0], w1 = pw2[1];
                     fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
                 }
             }
+            double *Tv = Tw + 32 * TSTR;
             auto fillWV = [&](int buf, int J) {
 #pragma unroll
                 for (int n = 0; n < SV; ++n) {
@@ -514,10 +529,27 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                 }
             };
             __syncthreads();
-            if (act) issue_tile(I, Jt);
+            if (act) {
+                issue_tile(I, Jt, 0);
+                // V_I: panel columns k = 0..31, rows 32 I .. 32 I + 31
+                const double *src = Vp + (size_t)(lane >> 4) * np + 32 * I + (lane & 15) * 2;
+                double *dst = Tv + (lane >> 4) * TSTR + (lane & 15) * 2;
+#pragma unroll 1
+                for (int k = 0; k < 16; ++k) {
+                    cp_async16_t(dst, src);
+                    src += 2 * (size_t)np;
+                    dst += 2 * TSTR;
+                }
+            }
             fillWV(0, Jt);
             cp_async_wait_all_t();
+            __syncwarp();
+            if (act) {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) Tv[lane * TSTR + r] = -Tv[lane * TSTR + r];
+            }
             __syncthreads();
+            const double *tv = Tv + tig * TSTR + 4 * grp;
             const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
             for (int J = Jt; J <= Jmax; ++J) {
                 const int buf = (J - Jt) & 1;
@@ -535,19 +567,23 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                 }
                 __syncwarp();
                 if (J + 1 <= Jmax) {
-                    if (act && J + 1 <= I) issue_tile(I, J + 1);
+                    if (act && J + 1 <= I) issue_tile(I, J + 1, 0);
                     fillWV(buf ^ 1, J + 1);
                 }
                 if (work) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
+                        const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
+                        const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
+                        const double fv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
                         for (int y = 0; y < 4; ++y) {
                             const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
                             const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
 #pragma unroll
                             for (int x = 0; x < 4; ++x) {
-                                dmma_t(c0[x][y], c1[x][y], fv[x][ks], bw);
+                                dmma_t(c0[x][y], c1[x][y], fv[x], bw);
                                 dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
                             }
                         }
@@ -956,13 +992,13 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     if (!S.L.two_stage) { arcb200_set_error("sy2sb: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
-    const int warps = ev ? atoi(ev) : (nmat > 148 ? 4 : 8);
+    const int warps = ev ? atoi(ev) : 8;
     if (warps == 4) {
-        const size_t smem = (4 * 32 * 36 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
+        const size_t smem = (2 * 4 * 32 * 36 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<4><<<nmat, 128, smem, st>>>(a);
     } else {
-        const size_t smem = (8 * 32 * 36 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
+        const size_t smem = (2 * 8 * 32 * 36 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<8><<<nmat, 256, smem, st>>>(a);
     }
