@@ -695,6 +695,103 @@ __global__ void __launch_bounds__(TS_THREADS, 1) sb2st_kernel(TsArgs a)
             if (lane == 0) tau2[(size_t)s * TM + t] = tau;
             const int r2 = r + L;
             const int L2 = min(32, N - r2);
+            if (L == 32 && L2 == 32 && tau != 0.0) {
+                // ---- interior step, all blocks full: one base pointer, constant offsets, no
+                // divergent regions.  Element (r + lane, r + j) sits at cp[j * CS]; the block
+                // below, element (r + 32 + lane, r + j), at cp[32 + j * CS].
+                constexpr int CS = EIG_LDB - 1;
+                double *cp = Bd + (size_t)r * EIG_LDB + lane;
+                double Dl[32], El[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) Dl[j] = (j <= lane) ? cp[j * CS] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) El[j] = cp[32 + j * CS];
+                vs[lane] = v;
+                __syncwarp();
+                const double2 *vs2 = reinterpret_cast<const double2 *>(vs);
+                const double2 *ws2 = reinterpret_cast<const double2 *>(ws);
+                double pd0 = 0.0, pd1 = 0.0, pd2 = 0.0, pd3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const double2 a = vs2[j / 2], b = vs2[j / 2 + 1];
+                    pd0 += Dl[j] * a.x;
+                    pd1 += Dl[j + 1] * a.y;
+                    pd2 += Dl[j + 2] * b.x;
+                    pd3 += Dl[j + 3] * b.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = Dl[j] * v;      // entries j > lane are zero
+                tile[lane * 33 + lane] = 0.0;                                       // the diagonal is in pd
+                __syncwarp();
+                double pt0 = 0.0, pt1 = 0.0, pt2 = 0.0, pt3 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    pt0 += tile[i * 33 + lane];
+                    pt1 += tile[(i + 1) * 33 + lane];
+                    pt2 += tile[(i + 2) * 33 + lane];
+                    pt3 += tile[(i + 3) * 33 + lane];
+                }
+                __syncwarp();
+                const double pv = tau * (((pd0 + pd1) + (pd2 + pd3)) + ((pt0 + pt1) + (pt2 + pt3)));
+                const double al = 0.5 * tau * warp_sum(pv * v);
+                const double w = pv - al * v;
+                ws[lane] = w;
+                __syncwarp();
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const double2 a = vs2[j / 2], b = ws2[j / 2];
+                    const double x0 = Dl[j] - (v * b.x + w * a.x);
+                    const double x1 = Dl[j + 1] - (v * b.y + w * a.y);
+                    if (j <= lane) cp[j * CS] = x0;
+                    if (j + 1 <= lane) cp[(j + 1) * CS] = x1;
+                    if (j & 2) { y2 += El[j] * a.x; y3 += El[j + 1] * a.y; } else { y0 += El[j] * a.x; y1 += El[j + 1] * a.y; }
+                }
+                const double y = tau * ((y0 + y1) + (y2 + y3));
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const double2 a = vs2[j / 2];
+                    El[j] -= y * a.x;
+                    El[j + 1] -= y * a.y;
+                }
+                double v2, tau_n, beta2;
+                warp_house(El[0], lane, v2, tau_n, beta2);
+                El[0] = (lane == 0) ? beta2 : 0.0;
+                __syncwarp();
+                if (tau_n != 0.0) {
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) tile[lane * 33 + j] = v2 * El[j];
+                    __syncwarp();
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        s0 += tile[i * 33 + lane];
+                        s1 += tile[(i + 1) * 33 + lane];
+                        s2 += tile[(i + 2) * 33 + lane];
+                        s3 += tile[(i + 3) * 33 + lane];
+                    }
+                    ws[lane] = ((s0 + s1) + (s2 + s3)) * tau_n;
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 2; j < 32; j += 2) {
+                        const double2 b = ws2[j / 2];
+                        El[j] -= v2 * b.x;
+                        El[j + 1] -= v2 * b.y;
+                    }
+                    El[1] -= v2 * ws[1];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cp[32 + j * CS] = El[j];
+                __syncwarp();
+                r = r2; L = L2; v = v2; tau = tau_n;
+                ++t;
+                __threadfence_block();
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) prog[s & 63] = s * 4096 + t;
+                wait_for(t);
+                continue;
+            }
             double Dl[32], El[32];
             if (tau != 0.0) {
 #pragma unroll
