@@ -248,7 +248,7 @@ def bench_c3(args, rank, world):
         roof = {"bound": "tensor", "kernel": "sy2sb_kernel (dense -> band reduction: panel QR + symmetric product "
                 "+ rank-2k update on FP64 tensor cores, mma.sync.m8n8k4.f64)",
                 "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-                "traffic": load_traffic("sy2sb_c3"),
+                "traffic": (load_traffic("sy2sb_c3_per_matrix") or 0.0) * nb or None,
                 "peak_source": "measured in this run: register-only mma.sync.m8n8k4.f64 loop, 8 warps/SM "
                                "(arcb200_dmma_peak); MEASURED_PEAKS.json has no FP64 figure (bf16 %s TFLOP/s, HBM %s GB/s)"
                                % (peaks_raw().get("bf16_tflops"), hbm),
