@@ -85,6 +85,9 @@ class AlkaliAtom:
         # cancelling elements (|value| < 1e-4 sqrt(<r^p>_a <r^p>_b)) by up to 3e-12 of that scale.
         # Default off: the one-warp-per-pair kernel reproduces the reference's formula exactly.
         self.fast_radial = False
+        # shard_radial=True (opt-in, collective): tables of >= 1024 new elements are sharded over
+        # the ranks of the default torch.distributed group and all-gathered (radial.sharded_table)
+        self.shard_radial = False
         self.gram_threshold = 64
 
     # pickling support (saveCalculation, alkali_atom_functions.py:4136-4278): plain data only
@@ -249,7 +252,10 @@ class AlkaliAtom:
                 pair_rows[t, slot] = index[st]
             pair_rows[t, 2] = power
         rb = _radial.RadialBatch(np.array(states), normalise=True, device=self.device)
-        if not self.fast_radial or len(todo) < self.gram_threshold:
+        if getattr(self, "shard_radial", False) and len(todo) >= 1024:
+            # collective: every rank of the default process group builds the same table
+            vals = rb.integrals_sharded(pair_rows).cpu().numpy()
+        elif not self.fast_radial or len(todo) < self.gram_threshold:
             vals = rb.integrals(pair_rows)               # one warp per pair
         else:
             # tensor-core path: one Gram block per ((l,j) of state a, (l,j) of state b, power)

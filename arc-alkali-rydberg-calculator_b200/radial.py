@@ -27,6 +27,21 @@ def make_state(innerLimit, outerLimit, step, init1, init2, l, s, j, stateEnergy,
     return rec
 
 
+def sharded_table(compute, pairs, group=None):
+    """One matrix-element table for all ranks of the process group: rank g evaluates the
+    contiguous shard pairs[g*P/G:(g+1)*P/G] with `compute(shard) -> tensor[len(shard)]` and
+    the shards are all-gathered once (NCCL over NVLink on GPUs, gloo in the CPU tests), so the
+    table is computed once per box instead of once per GPU.  Collective: every
+    rank must call it with the same `pairs`."""
+    from . import sweep
+    rank, world = sweep.dist_info(group)
+    if world == 1:
+        return compute(pairs)
+    lo, hi = sweep.shard_bounds(len(pairs), rank, world)
+    local = compute(pairs[lo:hi])
+    return sweep.gather_rows(local, len(pairs), group)
+
+
 class RadialBatch:
     """Wavefunctions of `states` (structured array of arcb200_state_t) on the GPU."""
 
@@ -89,6 +104,12 @@ class RadialBatch:
 
     def integrals(self, pairs):
         return self.integrals_device(pairs).cpu().numpy()
+
+    def integrals_sharded(self, pairs, group=None):
+        """integrals_device with the pairs sharded over the ranks of `group` and the results
+        all-gathered (every rank holds all wavefunctions: Numerov is ~10 % of a table)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
+        return sharded_table(self.integrals_device, pairs, group)
 
     def gram_device(self, blocks):
         """blocks: list of (row_states, col_states, power).  Returns (out tensor, offsets):

@@ -142,10 +142,13 @@ def timed_steps(fn, steps, warmup, world):
 
 
 # --------------------------------------------------------------------------- workloads
-def build_c3():
-    """Rb 60S+60S pair basis through our own defineBasis (GPU radial table)."""
+def build_c3(shard_radial=False):
+    """Rb 60S+60S pair basis through our own defineBasis (GPU radial table; with several
+    ranks the table is sharded and all-gathered over NCCL instead of rebuilt per GPU)."""
     import arc_b200
-    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 60, 0, .5, 60, 0, .5, .5, .5)
+    atom = arc_b200.Rubidium()
+    atom.shard_radial = bool(shard_radial)
+    calc = arc_b200.PairStateInteractions(atom, 60, 0, .5, 60, 0, .5, .5, .5)
     calc.defineBasis(0., 0., 5, 5, 25e9)
     return calc
 
@@ -154,7 +157,7 @@ def bench_c3(args, rank, world):
     import torch
     from arc_b200 import sweep, _lib
     t0 = time.time()
-    calc = build_c3()
+    calc = build_c3(shard_radial=world > 1)
     t_define = time.time() - t0
     N = len(calc.basisStates)
     k = 250

@@ -66,3 +66,42 @@ def test_gather_rows_gloo_world2_ragged():
             assert full.shape == (npoints, 4)
             assert np.array_equal(full, want)
             assert np.array_equal(fi[:, 0, 0], np.arange(npoints))
+
+
+def _table_worker(rank, world, port, npairs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arc_b200 import radial
+        pairs = np.stack([np.arange(npairs), np.arange(npairs) + 1, 1 + np.arange(npairs) % 2], 1).astype(np.int32)
+        seen = []
+
+        def compute(shard):                      # stand-in for RadialBatch.integrals_device
+            seen.append(len(shard))
+            return torch.as_tensor(shard[:, 0] * 100.0 + shard[:, 1] + 0.5 * shard[:, 2], dtype=torch.float64)
+        full = radial.sharded_table(compute, pairs)
+        q.put((rank, full.numpy(), seen[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_radial_table_sharded_allgather_gloo_world2():
+    """Matrix-element table computed once per box: each rank evaluates its shard of the pair
+    list, the shards are all-gathered (NCCL on the GPUs)."""
+    npairs = 1001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_table_worker, args=(r, 2, port, npairs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    i = np.arange(npairs)
+    want = i * 100.0 + (i + 1) + 0.5 * (1 + i % 2)
+    assert sorted(o[2] for o in outs) == [500, 501]          # each rank computed only its shard
+    for rank, full, _n in outs:
+        assert np.array_equal(full, want)
