@@ -14,6 +14,7 @@ from .atoms import (AlkaliAtom, DivalentAtom, Hydrogen, Lithium6, Lithium7, Sodi
                     Ytterbium174)
 from .numerov import NumerovWavefunction, NumerovBack  # noqa: F401
 from .stark import StarkMap  # noqa: F401
+from .shirley import StarkBasisGenerator, ShirleyMethod  # noqa: F401
 from .pairstate import PairStateInteractions  # noqa: F401
 
 __version__ = "0.1.0"

@@ -261,6 +261,36 @@ __global__ void save_window_kernel(int N, int Npad, const double *base, size_t s
         out[e] = Z[(e % N) + (e / N) * Npad];
 }
 
+// Floquet (Shirley) transition probabilities: for every atomic basis state a
+//   P[f][a] = sum_k sum_i |Z[k*dim0 + a, i]|^2 * hl[f][i],   hl[f][i] = |Z[target, i]|^2
+// (calculations_atom_single.py:3944-3949).  Thread <-> matrix row (coalesced along the rows of
+// the column-major eigenvector matrix), the Floquet blocks are folded with atomics.
+// grid = (ceil(N/256), nmat); d_tp must be zeroed.
+__global__ void __launch_bounds__(256) transprob_kernel(int N, int Npad, const double *base, size_t slot,
+                                                        size_t oQ, int dim0, const double *__restrict__ d_hl,
+                                                        double *__restrict__ d_tp, int f0)
+{
+    __shared__ double sh[256];
+    const int mat = blockIdx.y;
+    const double *Z = base + (size_t)mat * slot + oQ;
+    const double *hl = d_hl + (size_t)(f0 + mat) * N;
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    double acc = 0.0;
+    for (int i0 = 0; i0 < N; i0 += 256) {
+        __syncthreads();
+        sh[threadIdx.x] = (i0 + threadIdx.x < N) ? hl[i0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        if (r < N) {
+            const int n = min(256, N - i0);
+            for (int i = 0; i < n; ++i) {
+                const double z = Z[r + (size_t)(i0 + i) * Npad];
+                acc += z * z * sh[i];
+            }
+        }
+    }
+    if (r < N) atomicAdd(&d_tp[(size_t)(f0 + mat) * dim0 + (r % dim0)], acc);
+}
+
 int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma,
                 cudaStream_t st, int *launches)
 {
@@ -303,11 +333,12 @@ extern "C" int arcb200_scatter_coo(int device, void *stream, int32_t N, int64_t 
     return 0;
 }
 
-extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
-                                   const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
-                                   const double *d_drive_w, int32_t topk, double contrib_max,
-                                   double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
-                                   void *d_work, int64_t wbytes, int32_t batch)
+static int stark_sweep_impl(int device, void *stream, int32_t N, const double *d_h0diag,
+                            const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
+                            const double *d_drive_w, int32_t topk, double contrib_max,
+                            double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
+                            void *d_work, int64_t wbytes, int32_t batch, int32_t dim0,
+                            double *d_tprob)
 {
     if (nF <= 0) return 0;
     if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
@@ -318,6 +349,7 @@ extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const do
     const WorkView W = carve(d_work, L, batch);
     const int ntiles = L.NB * (L.NB + 1) / 2;
     int launches = 0;
+    if (d_tprob) ARCB200_CUDA_CHECK(cudaMemsetAsync(d_tprob, 0, (size_t)nF * dim0 * sizeof(double), st));
     for (int f0 = 0; f0 < nF; f0 += batch) {
         const int nmat = min(batch, nF - f0);
         assemble_stark_kernel<<<dim3(ntiles, nmat), 256, 0, st>>>(
@@ -325,15 +357,39 @@ extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const do
         ++launches;
         int rc = solve_batch(W, nmat, N, false, 0.0, st, &launches);
         if (rc) return rc;
-        const int tk = topk > 0 ? topk : 1;
         epilogue_kernel<<<dim3((N + 7) / 8, nmat), 256, 0, st>>>(
             N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, nullptr, N, idx0, d_drive_w,
             topk > 0 ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, f0);
-        (void)tk;
         ++launches;
+        if (d_tprob) {
+            transprob_kernel<<<dim3((N + 255) / 256, nmat), 256, 0, st>>>(
+                N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, dim0, d_hl, d_tprob, f0);
+            ++launches;
+        }
     }
     ARCB200_LAUNCH_CHECK("stark sweep");
     return launches;
+}
+
+extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
+                                   const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
+                                   const double *d_drive_w, int32_t topk, double contrib_max,
+                                   double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
+                                   void *d_work, int64_t wbytes, int32_t batch)
+{
+    return stark_sweep_impl(device, stream, N, d_h0diag, d_V, nF, d_F, idx0, d_drive_w, topk,
+                            contrib_max, d_y, d_hl, d_comp_c, d_comp_i, d_work, wbytes, batch, 0,
+                            nullptr);
+}
+
+extern "C" int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_t dim0,
+                                     const double *d_h0diag, const double *d_B, int32_t nF,
+                                     const double *d_F, int32_t idx0, double *d_y, double *d_hl,
+                                     double *d_tprob, void *d_work, int64_t wbytes, int32_t batch)
+{
+    if (dim0 <= 0 || N % dim0 != 0) { arcb200_set_error("floquet_sweep: N must be a multiple of dim0"); return -1; }
+    return stark_sweep_impl(device, stream, N, d_h0diag, d_B, nF, d_F, idx0, nullptr, 0, 2.0, d_y,
+                            d_hl, nullptr, nullptr, d_work, wbytes, batch, dim0, d_tprob);
 }
 
 extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,

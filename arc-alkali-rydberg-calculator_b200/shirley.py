@@ -1,0 +1,251 @@
+"""StarkBasisGenerator / ShirleyMethod -- drop-in for the Floquet Stark maps of
+arc.calculations_atom_single (3172-3982).
+
+Same constructor, `defineBasis`, `defineShirleyHamiltonian` and `diagonalise` signatures and
+result attributes as the reference.  The basis and the bare matrices (`bareEnergies`, `V`) are
+built on the host from the batched GPU radial table; the Floquet Hamiltonians
+    Hf = H0 + dT*freq + B*eField,   dimension dim0 * (2 fn + 1)
+are assembled and diagonalised on the GPU (arcb200_floquet_sweep: the same assembly kernel and
+batched eigensolver as StarkMap, plus a kernel that folds the Floquet blocks into the
+long-time-averaged transition probabilities), one batched sweep over the fields per frequency.
+No CPU fallback.
+"""
+import warnings
+
+import numpy as np
+from scipy.constants import physical_constants, h as C_h, e as C_e
+
+from . import sweep as _sweep
+from .stark import efield_angular
+
+
+class StarkBasisGenerator:
+    """Basis |n l j mj> and the bare Stark matrices (calculations_atom_single.py:3172-3668)."""
+
+    def __init__(self, atom):
+        self.atom = atom
+        self.n = self.l = self.j = self.mj = self.s = None
+        self.basisStates = []
+        self.indexOfCoupledState = None
+        self.targetState = []
+        self.targetEnergy = None
+        self.bareEnergies = []
+        self.nMin = self.nMax = self.maxL = self.Bz = self.q = None
+        self.H = []
+        self.V = []
+        self.eFieldCouplingSaved = False
+        self.gpu_kernel_launches = 0
+
+    def _eFieldCouplingDivE(self, n1, l1, j1, mj1, n2, l2, j2, mj2, s=0.5):
+        """calculations_atom_single.py:3294-3311."""
+        if (abs(mj1 - mj2) > 0.1) or (abs(l1 - l2) != 1):
+            return 0
+        result = (self.atom.getRadialMatrixElement(n1, l1, j1, n2, l2, j2, s=s)
+                  * physical_constants["Bohr radius"][0] * C_e)
+        return result * efield_angular(l1, j1, mj1, l2, j2, mj2, s=s)
+
+    def _eFieldCoupling(self, n1, l1, j1, mj1, n2, l2, j2, mj2, eField, s=0.5):
+        return self._eFieldCouplingDivE(n1, l1, j1, mj1, n2, l2, j2, mj2, s=s) * eField
+
+    def _onePhotonCoupling(self, ns, ls, js, mjs, nt, lt, jt, mjt, q, s=0.5):
+        """calculations_atom_single.py:3318-3355."""
+        if (ns == nt) and (ls == lt) and (js == jt) and (mjs == mjt):
+            return False
+        elif (abs(ls - lt) == 1) and (mjt - mjs == q):
+            if ls - lt == js - jt:
+                return True
+            elif (js == jt) and ((js == ls + s) or (jt == lt + s)):
+                return True
+            return False
+        return False
+
+    def _twoPhotonCoupling(self, ns, ls, js, mjs, nt, lt, jt, mjt, q, s=0.5):
+        """calculations_atom_single.py:3357-3394."""
+        if (ns == nt) and (ls == lt) and (js == jt) and (mjs == mjt):
+            return False
+        elif (abs(ls - lt) == 2) and (ls - lt == js - jt) and ((mjt - mjs) / 2 == q):
+            return True
+        elif ((ls - lt) == 0) and (js == jt) and ((mjt - mjs) / 2 == q):
+            return True
+        return False
+
+    def defineBasis(self, n, l, j, mj, q=0, nMin=None, nMax=None, maxL=None, Bz=0, edN=0,
+                    basisStates=None, progressOutput=False, debugOutput=False, s=0.5):
+        """calculations_atom_single.py:3396-3487."""
+        self.n, self.l, self.j, self.mj, self.Bz, self.s = n, l, j, mj, Bz, s
+        if basisStates is not None:
+            self._defineBasisStates(basisStates)
+        elif nMin is not None and nMax is not None and maxL is not None:
+            self.q = q
+            if edN in [0, 1, 2]:
+                self.edN = edN
+            else:
+                raise ValueError("edN must be 0, 1, or 2")
+            self.nMin, self.nMax, self.maxL = nMin, nMax, maxL
+            self._findBasisStates(progressOutput, debugOutput)
+        else:
+            raise ValueError("Input arguments are not complete. "
+                             + "Either specify nMin, nMax, maxL or basisStates")
+        self._buildHamiltonian(progressOutput, debugOutput)
+
+    def _defineBasisStates(self, states_list):
+        """calculations_atom_single.py:3489-3504."""
+        self.basisStates = states_list
+        t_state = [self.n, self.l, self.j, self.mj]
+        try:
+            self.indexOfCoupledState = states_list.index(t_state)
+        except ValueError:
+            raise ValueError(f"Target state {t_state} not in states list")
+        self.targetState = states_list[self.indexOfCoupledState]
+
+    def _findBasisStates(self, progressOutput=False, debugOutput=False):
+        """calculations_atom_single.py:3506-3582 (same enumeration order)."""
+        states = []
+        n, l, j, mj, q, s, edN = self.n, self.l, self.j, self.mj, self.q, self.s, self.edN
+        indexOfCoupledState = 0
+        index = 0
+        for tn in range(self.nMin, self.nMax + 1):
+            for tl in range(min(self.maxL + 1, tn)):
+                for tj in np.linspace(tl - s, tl + s, round(2 * s + 1)):
+                    if abs(mj + q) - 0.1 > tj:
+                        continue
+                    if (n == tn) and (l == tl) and (j == tj):
+                        states.append([tn, tl, tj, mj])
+                        indexOfCoupledState = index
+                    elif (edN == 0) and (tn >= self.atom.groundStateN
+                                         or [tn, tl, tj] in self.atom.extraLevels):
+                        states.append([tn, tl, tj, mj + q])
+                        index += 1
+                    elif (edN == 1 or edN == 2) and self._onePhotonCoupling(
+                            n, l, j, mj, tn, tl, tj, mj + q, q, s):
+                        states.append([tn, tl, tj, mj + q])
+                        index += 1
+                    elif edN == 2 and self._twoPhotonCoupling(
+                            n, l, j, mj, tn, tl, tj, mj + 2 * q, q, s):
+                        states.append([tn, tl, tj, mj + 2 * q])
+                        index += 1
+        if progressOutput:
+            print("Found ", len(states), " states.")
+        self.basisStates = states
+        self.indexOfCoupledState = indexOfCoupledState
+        self.targetState = states[indexOfCoupledState]
+
+    def _buildHamiltonian(self, progressOutput=False, debugOutput=False):
+        """calculations_atom_single.py:3584-3668: `bareEnergies` (Hz) and `V` (Hz/(V/m),
+        half the coupling; the angular factor is taken at `self.mj` for both states like the
+        reference).  All radial elements come from one GPU batch."""
+        states = self.basisStates
+        dimension = len(states)
+        by_l = {}
+        for idx, st in enumerate(states):
+            by_l.setdefault(st[1], []).append(idx)
+        pairs = [(a, b) for l1, idxs in by_l.items() for b in by_l.get(l1 + 1, []) for a in idxs]
+        want = [(states[a][0], states[a][1], states[a][2],
+                 states[b][0], states[b][1], states[b][2]) for a, b in pairs]
+        before = self.atom.gpu_kernel_launches
+        if getattr(self.atom, "divalent", False):
+            self.atom.precompute_radial(dipole_pairs=want, s=self.s)
+        else:
+            self.atom.precompute_radial(dipole_pairs=want)
+        self.gpu_kernel_launches += self.atom.gpu_kernel_launches - before
+
+        self.bareEnergies = np.zeros((dimension), dtype=np.double)
+        self.V = np.zeros((dimension, dimension), dtype=np.double)
+        for ii in range(dimension):
+            self.bareEnergies[ii] = (
+                self.atom.getEnergy(states[ii][0], states[ii][1], states[ii][2], s=self.s)
+                * C_e / C_h
+                + self.atom.getZeemanEnergyShift(states[ii][1], states[ii][2], states[ii][3],
+                                                 self.Bz, s=self.s) / C_h)
+        ang = {}
+        for a, b in pairs:
+            ii, jj = (a, b) if a < b else (b, a)
+            k = (states[ii][1], states[ii][2], states[jj][1], states[jj][2])
+            if k not in ang:
+                ang[k] = efield_angular(states[ii][1], states[ii][2], self.mj,
+                                        states[jj][1], states[jj][2], self.mj, s=self.s)
+            coupling = 0.5 * (self.atom.getRadialMatrixElement(
+                states[ii][0], states[ii][1], states[ii][2],
+                states[jj][0], states[jj][1], states[jj][2], s=self.s)
+                * physical_constants["Bohr radius"][0] * C_e * ang[k]) / C_h
+            self.V[jj][ii] = coupling
+            self.V[ii][jj] = coupling
+        self.H = np.diag(self.bareEnergies)
+        self.targetEnergy = self.bareEnergies[self.indexOfCoupledState]
+
+
+class ShirleyMethod(StarkBasisGenerator):
+    """Shirley's time-independent Floquet Hamiltonian (calculations_atom_single.py:3671-3982)."""
+
+    def __init__(self, atom):
+        super().__init__(atom)
+        self.fn = None
+        self.H0 = self.B = self.dT = []
+        self.eFields = self.freqs = None
+        self.eigs, self.eigVectors, self.transProbs, self.targetShifts = [], [], [], []
+
+    def defineShirleyHamiltonian(self, fn, debugOutput=False):
+        """calculations_atom_single.py:3795-3852: `H0`, `dT`, `B` as scipy CSR like the
+        reference (the GPU path reads their diagonals / dense form)."""
+        import scipy.sparse as sp
+        self.fn = fn
+        if not fn >= 1:
+            raise ValueError("Floquet expansion must be greater than 1."
+                             + " Rank of 0 is equivalent to rotating wave approximation"
+                             + " solution and is not covered by this method.")
+        dimension = len(self.bareEnergies)
+        self.H0 = sp.diags(np.tile(self.bareEnergies, 2 * fn + 1)).tocsr()
+        self.dT = sp.block_diag([sp.diags([float(i)], 0, shape=(dimension, dimension))
+                                 for i in range(-fn, fn + 1, 1)], dtype=np.double).tocsr()
+        self.B = sp.bmat([[self.V if abs(i - j) == 1 else None for i in range(-fn, fn + 1, 1)]
+                          for j in range(-fn, fn + 1, 1)], dtype=np.double).tocsr()
+
+    def diagonalise(self, eFields, freqs, progressOutput=False, debugOutput=False,
+                    keepEigenvectors=False, batch=None):
+        """calculations_atom_single.py:3854-3982.  Results `eigs`, `transProbs`,
+        `targetShifts` with the reference's shapes (outer product of the inputs, singleton
+        dimensions squeezed).  `eigVectors` (dim x dim per point -- 107 MB per point at the
+        documented 2583 basis) is only filled with `keepEigenvectors=True`; the transition
+        probabilities and shifts are computed on the GPU without it."""
+        dim0 = len(self.basisStates)
+        dim1 = 2 * self.fn + 1
+        N = dim0 * dim1
+        refInd = self.fn * dim0
+        tarInd = self.indexOfCoupledState + refInd
+        self.eFields = np.array(eFields, ndmin=1)
+        self.freqs = np.array(freqs, ndmin=1)
+        fields = np.asarray(self.eFields, dtype=np.float64).reshape(-1)
+        fr = np.asarray(self.freqs, dtype=np.float64).reshape(-1)
+        eig = np.zeros((len(fields), len(fr), N), dtype=np.double)
+        transProbs = np.zeros((len(fields), len(fr), dim0), dtype=np.double)
+        targetShifts = np.zeros((len(fields), len(fr)), dtype=np.double)
+        eigVec = np.zeros((len(fields), len(fr), N, N), dtype=np.complex128) if keepEigenvectors else []
+        h0 = np.tile(np.asarray(self.bareEnergies, dtype=np.float64), dim1)
+        kblock = np.repeat(np.arange(-self.fn, self.fn + 1, dtype=np.float64), dim0)
+        Bd = self.B.toarray()
+        import torch
+        device = getattr(self.atom, "device", None)
+        from . import _lib
+        dev = torch.device("cuda", _lib.require_device(device))
+        d_B = torch.as_tensor(np.ascontiguousarray(Bd)).to(dev)
+        for fi, freq in enumerate(fr):
+            hdiag = h0 + kblock * freq                        # H0 + dT * freq
+            y, hl, tp, launches = _sweep.floquet_sweep(hdiag, None, fields, tarInd, dim0,
+                                                       device=device, batch=batch, d_B=d_B)
+            self.gpu_kernel_launches += launches
+            eig[:, fi, :] = y
+            transProbs[:, fi, :] = tp
+            for ei in range(len(fields)):
+                evInd = int(np.argmax(hl[ei]))
+                if np.count_nonzero(y[ei] == y[ei][evInd]) > 1:
+                    warnings.warn("Multiple states have same overlap with target. Only saving first one.")
+                targetShifts[ei, fi] = self.targetEnergy - y[ei][evInd]
+            if keepEigenvectors:
+                Hs = np.stack([np.diag(hdiag) + Bd * f for f in fields])
+                _w, v = _sweep.syevd_batched(Hs, device=device)
+                eigVec[:, fi] = v
+        shp = (*self.eFields.shape, *self.freqs.shape)
+        self.eigs = eig.reshape(*shp, N).squeeze()
+        self.transProbs = transProbs.reshape(*shp, dim0).squeeze()
+        self.targetShifts = targetShifts.reshape(shp).squeeze()
+        self.eigVectors = eigVec.reshape(*shp, N, N).squeeze() if keepEigenvectors else []

@@ -122,6 +122,34 @@ def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
     return res
 
 
+def floquet_sweep(h0diag, B, fields, idx0, dim0, device=None, batch=None, d_B=None):
+    """Solve H = diag(h0) + F*B for every F and fold the Floquet blocks into transition
+    probabilities (calculations_atom_single.py:3931-3957).  Returns (y, hl, tprob) as numpy
+    arrays [nF, N], [nF, N], [nF, dim0].  `d_B` may carry B already resident on the device
+    (it does not change between drive frequencies)."""
+    import torch
+    lib = _lib.load()
+    device = _lib.require_device(device)
+    dev = torch.device("cuda", device)
+    fields = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1)
+    nF, N = len(fields), int(len(h0diag))
+    d_h0 = torch.as_tensor(np.ascontiguousarray(h0diag, dtype=np.float64)).to(dev)
+    if d_B is None:
+        d_B = torch.as_tensor(np.ascontiguousarray(B, dtype=np.float64)).to(dev)
+    d_F = torch.as_tensor(fields).to(dev)
+    y = torch.empty((nF, N), dtype=torch.float64, device=dev)
+    hl = torch.empty((nF, N), dtype=torch.float64, device=dev)
+    tp = torch.empty((nF, dim0), dtype=torch.float64, device=dev)
+    b = _pick_batch(N, nF, N, device, batch)
+    wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, N))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rc = lib.arcb200_floquet_sweep(device, _lib.stream_ptr(device), N, int(dim0), _lib.ptr(d_h0),
+                                   _lib.ptr(d_B), nF, _lib.ptr(d_F), int(idx0), _lib.ptr(y),
+                                   _lib.ptr(hl), _lib.ptr(tp), _lib.ptr(work), wbytes, b)
+    _lib.check(rc, "arcb200_floquet_sweep")
+    return y.cpu().numpy(), hl.cpu().numpy(), tp.cpu().numpy(), rc
+
+
 class PairOperators:
     """matDiagonal + dense matR[o] staged once on the device (scatter of the COO
     entries; the reference keeps scipy CSR, calculations_atom_pairstate.py:3222-3239)."""

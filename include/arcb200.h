@@ -142,6 +142,18 @@ int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0d
                         double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
                         void *d_work, int64_t work_bytes, int32_t batch);
 
+/* Floquet (Shirley) sweep: for every field amplitude F[f]:  H = diag(h0) + F[f]*B, N = dim0 *
+ * (2 fn + 1) (the caller folds the drive frequency into h0 = tile(bareEnergies) + k*freq),
+ * full eigendecomposition, then
+ *   y[f][i]  = eigenvalue i (ascending),  hl[f][i] = |v[idx0,i]|^2,
+ *   tprob[f][a] = sum_k sum_i |v[k*dim0 + a, i]|^2 |v[idx0, i]|^2   (a < dim0)
+ * Replaces the loop body of ShirleyMethod.diagonalise
+ * (calculations_atom_single.py:3931-3957; Shirley, Phys. Rev. 138, B979, eq. 19). */
+int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_t dim0,
+                          const double *d_h0diag, const double *d_B, int32_t nF,
+                          const double *d_F, int32_t idx0, double *d_y, double *d_hl,
+                          double *d_tprob, void *d_work, int64_t work_bytes, int32_t batch);
+
 /* Pair-state sweep: for every distance R[p] (micrometres):
  *   H = diag(h0) + sum_o M_o / (R*1e-6)^(3+o)      (M_o dense N x N, o < norders)
  * d_M = DEVICE array of norders device pointers to the dense row-major M_o.

@@ -399,6 +399,41 @@ def gen_c6(arc):
     print("c6 golden", [(o["atom"], o["args"][0], o["value"]) for o in out])
 
 
+def gen_shirley(arc):
+    """ShirleyMethod (Floquet Stark maps, calculations_atom_single.py:3172-3982):
+    small Rb bases, full manifold (edN=0) and dipole-limited (edN=2), fn = 1 and 2."""
+    rb = arc.Rubidium()
+    cases = [
+        dict(name="a", basis=(30, 0, 0.5, 0.5), kw=dict(q=0, nMin=28, nMax=32, maxL=3, edN=0), fn=1,
+             eFields=[0.0, 50.0, 200.0], freqs=[1.0e9, 6.0e9]),
+        dict(name="b", basis=(30, 2, 2.5, 0.5), kw=dict(q=1, nMin=27, nMax=33, maxL=5, edN=2, Bz=1e-4), fn=2,
+             eFields=[100.0], freqs=[2.0e9, 3.5e9, 10.0e9]),
+    ]
+    out = {}
+    for c in cases:
+        t0 = time.time()
+        calc = arc.ShirleyMethod(rb)
+        calc.defineBasis(*c["basis"], **c["kw"])
+        calc.defineShirleyHamiltonian(fn=c["fn"])
+        calc.diagonalise(c["eFields"], c["freqs"])
+        k = c["name"]
+        out[k + "_basis"] = np.array(c["basis"], dtype=float)
+        out[k + "_kw"] = np.array([c["kw"].get("q", 0), c["kw"]["nMin"], c["kw"]["nMax"], c["kw"]["maxL"],
+                                   c["kw"]["edN"], c["kw"].get("Bz", 0.0), c["fn"]], dtype=float)
+        out[k + "_eFields"] = np.array(c["eFields"], dtype=float)
+        out[k + "_freqs"] = np.array(c["freqs"], dtype=float)
+        out[k + "_basisStates"] = np.array(calc.basisStates, dtype=float)
+        out[k + "_index"] = calc.indexOfCoupledState
+        out[k + "_bareEnergies"] = np.array(calc.bareEnergies)
+        out[k + "_V"] = np.array(calc.V)
+        out[k + "_eigs"] = np.array(calc.eigs)
+        out[k + "_transProbs"] = np.array(calc.transProbs)
+        out[k + "_targetShifts"] = np.array(calc.targetShifts)
+        print("shirley", k, "dim0", len(calc.basisStates), "eigs", np.array(calc.eigs).shape,
+              "%.1fs" % (time.time() - t0))
+    np.savez_compressed(os.path.join(GOLD, "shirley_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -422,3 +457,5 @@ if __name__ == "__main__":
         gen_sorted(arc)
     if "c6" in what:
         gen_c6(arc)
+    if "shirley" in what:
+        gen_shirley(arc)
