@@ -419,6 +419,52 @@ def bench_c1(args):
                              "sample": "%d of the 600 fields: numpy.linalg.eigh + highlight + _stateComposition2" % nf}}
 
 
+def bench_shirley(args):
+    """The one workload with a published reference timing (doc/AC_Stark_primer.ipynb:597-644,
+    SURVEY.md section 6): Rb85 56D5/2 mj=1/2, n=46..66, l<=20 (861 states as printed in the
+    notebook), Floquet rank 1 (3 x 861 = 2583),
+    100 field amplitudes at 12.3 GHz -- 2 min 13 s wall in the notebook (hardware unstated)."""
+    import torch
+    import arc_b200
+    t0 = time.perf_counter()
+    calc = arc_b200.ShirleyMethod(arc_b200.Rubidium85())
+    calc.defineBasis(56, 2, 2.5, 0.5, 0, 46, 66, 20)
+    calc.defineShirleyHamiltonian(fn=1)
+    t_def = time.perf_counter() - t0
+    E = np.geomspace(1e0, 1.2e1, 100)
+    freq = 12.3e9
+    ts = []
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        calc.diagonalise(E, freq)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts[1:]))
+    dim0 = len(calc.basisStates)
+    N = 3 * dim0
+    # CPU sample: the reference's loop body (dense eigh + transition probabilities) on 2 points
+    tar = calc.indexOfCoupledState + dim0
+    t0 = time.perf_counter()
+    err = 0.0
+    for ei in (0, 99):
+        Hf = (calc.H0 + calc.dT * freq + calc.B * E[ei]).toarray()
+        ev, vec = np.linalg.eigh(Hf)
+        tp = (np.abs(vec * vec[tar]) ** 2).reshape((3, dim0, N)).sum(axis=(0, -1))
+        err = max(err, float(np.abs(calc.eigs[ei] - ev).max() / np.abs(ev).max()),
+                  float(np.abs(calc.transProbs[ei] - tp).max()))
+    dt = (time.perf_counter() - t0) / 2
+    return {"workload": "shirley: Rb85 56D5/2 mj=1/2 ShirleyMethod fn=1, dim %d x 3 = %d, 100 fields x 1 frequency "
+                        "(doc/AC_Stark_primer.ipynb)" % (dim0, N),
+            "metric": "fp64_eigensolves_per_sec", "value": 100 / sec, "unit": "solves/s",
+            "s_per_sweep_e2e": sec, "defineBasis_s": t_def, "gpu_launches": calc.gpu_kernel_launches,
+            "max_err_vs_cpu_sample": err,
+            "published_reference": {"value": 100 / 133.0, "unit": "solves/s",
+                                    "source": "doc/AC_Stark_primer.ipynb:643-644 (wall 2 min 13 s, hardware unstated)"},
+            "cpu_baseline": {"value": 1.0 / dt, "unit": "solves/s", "cores": "default BLAS threads", "kind": "port",
+                             "sample": "2 of the 100 points: numpy.linalg.eigh + transition probabilities"}}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -503,6 +549,10 @@ def main():
                 sub["stark_c1"] = bench_c1(args)
             except Exception as ex:
                 sub["stark_c1"] = {"error": repr(ex)}
+            try:
+                sub["shirley_doc"] = bench_shirley(args)
+            except Exception as ex:
+                sub["shirley_doc"] = {"error": repr(ex)}
     barrier(world)
     if rank == 0:
         line = {
