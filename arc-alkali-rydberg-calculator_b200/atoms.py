@@ -311,8 +311,77 @@ class AlkaliAtom:
 
     def updateDipoleMatrixElementsFile(self):
         """No-op: the memo lives in memory (the reference dumps sqlite -> .npy here,
-        alkali_atom_functions.py:1860-1906)."""
+        alkali_atom_functions.py:1860-1906); see saveMatrixElementTables for the same files."""
         return None
+
+    # -------------------------------------------------- persistence in the reference's formats
+    def _memo_rows(self, memo):
+        """Rows of the reference's memo tables: alkali (n1,l1,j1_x2,n2,l2,j2_x2,value)
+        (alkali_atom_functions.py:275-283); divalent (n1,l1,j1,n2,l2,j2,s,value)
+        (divalent_atom_functions.py:164-171).  Lower-energy state first in both."""
+        return [tuple(float(x) for x in k) + (float(v),) for k, v in sorted(memo.items())]
+
+    def saveMatrixElementTables(self, dipole_path, quadrupole_path):
+        """Write the radial dipole / quadrupole memo as the `.npy` files stock ARC reads at start
+        (`*_dipole_matrix_elements.npy`, alkali_atom_functions.py:246-265, written by its
+        updateDipoleMatrixElementsFile, 1860-1906): float64[n, 7] (alkali) or [n, 8] (divalent)."""
+        width = 8 if getattr(self, "divalent", False) else 7
+        for path, memo in ((dipole_path, self._dipole), (quadrupole_path, self._quadrupole)):
+            rows = self._memo_rows(memo)
+            np.save(path, np.array(rows, dtype=np.float64).reshape(-1, width))
+
+    def loadMatrixElementTables(self, dipole_path=None, quadrupole_path=None):
+        """Read `.npy` tables in the reference's format into the memo (elements present are
+        never recomputed, like rows of the reference's sqlite memo).  Returns rows loaded."""
+        n = 0
+        for path, memo in ((dipole_path, self._dipole), (quadrupole_path, self._quadrupole)):
+            if path is None:
+                continue
+            data = np.load(path, allow_pickle=True, encoding="latin1")
+            for row in data:
+                memo[tuple(int(round(float(x))) for x in row[:-1])] = float(row[-1])
+                n += 1
+        return n
+
+    def exportToArcDatabase(self, db_path):
+        """Bulk-insert the memo into a SQLite file with the schema of the reference's
+        `precalculated` database (tables `dipoleME`, `quadrupoleME`; SURVEY.md 8b seam B2):
+        stock ARC pointed at it (`atom.conn`) answers these elements without running Numerov
+        (alkali_atom_functions.py:1057-1065).  Returns (dipole rows, quadrupole rows)."""
+        import sqlite3
+        div = getattr(self, "divalent", False)
+        cols = ("n1 TINYINT UNSIGNED, l1 TINYINT UNSIGNED, j1 TINYINT UNSIGNED, n2 TINYINT UNSIGNED, "
+                "l2 TINYINT UNSIGNED, j2 TINYINT UNSIGNED, s TINYINT UNSIGNED" if div else
+                "n1 TINYINT UNSIGNED, l1 TINYINT UNSIGNED, j1_x2 TINYINT UNSIGNED, n2 TINYINT UNSIGNED, "
+                "l2 TINYINT UNSIGNED, j2_x2 TINYINT UNSIGNED")
+        pk = "n1,l1,j1,n2,l2,j2,s" if div else "n1,l1,j1_x2,n2,l2,j2_x2"
+        conn = sqlite3.connect(db_path)
+        c = conn.cursor()
+        counts = []
+        for table, val, memo in (("dipoleME", "dme", self._dipole), ("quadrupoleME", "qme", self._quadrupole)):
+            c.execute("CREATE TABLE IF NOT EXISTS %s (%s, %s DOUBLE, PRIMARY KEY (%s))" % (table, cols, val, pk))
+            rows = [tuple(int(x) for x in k) + (float(v),) for k, v in memo.items()]
+            c.executemany("INSERT OR REPLACE INTO %s VALUES (%s)" % (table, ",".join("?" * (len(pk.split(",")) + 1))), rows)
+            counts.append(len(rows))
+        conn.commit()
+        conn.close()
+        return tuple(counts)
+
+    def importFromArcDatabase(self, db_path):
+        """Read `dipoleME` / `quadrupoleME` of a reference database into the memo."""
+        import sqlite3
+        conn = sqlite3.connect(db_path)
+        c = conn.cursor()
+        n = 0
+        for table, memo in (("dipoleME", self._dipole), ("quadrupoleME", self._quadrupole)):
+            c.execute("SELECT COUNT(*) FROM sqlite_master WHERE type='table' AND name=?", (table,))
+            if c.fetchone()[0] == 0:
+                continue
+            for row in c.execute("SELECT * FROM %s" % table):
+                memo[tuple(int(x) for x in row[:-1])] = float(row[-1])
+                n += 1
+        conn.close()
+        return n
 
     # -------------------------------------------------- angular parts of dipole elements
     def getReducedMatrixElementL(self, n1, l1, j1, n2, l2, j2, s=0.5):

@@ -113,3 +113,47 @@ def test_selection_rules_return_zero_without_compute():
     # literature value (rubidium_literature_dme.csv) is returned without any computation
     assert a.getRadialMatrixElement(5, 0, .5, 5, 1, .5) == a._lit[(5, 0, 1, 5, 1, 1)][0]
     assert a.gpu_kernel_launches == 0
+
+
+def test_memo_persistence_reference_formats(tmp_path):
+    """Radial memo <-> the reference's own table formats (SURVEY.md 8b seam B2, 8f rank 4):
+    `.npy` rows (n1,l1,j1_x2,n2,l2,j2_x2,value) and the sqlite tables dipoleME / quadrupoleME
+    (alkali_atom_functions.py:246-335, 1860-1906); divalent keys carry j and s
+    (divalent_atom_functions.py:164-171).  No GPU: the memo is filled by hand."""
+    import sqlite3
+    import arc_b200
+    a = arc_b200.Rubidium()
+    a._dipole[(60, 0, 1, 60, 1, 3)] = 4131.5
+    a._dipole[(59, 1, 1, 60, 0, 1)] = -3820.25
+    a._quadrupole[(60, 0, 1, 61, 2, 5)] = 1.25e6
+    d, q = str(tmp_path / "rb_dipole_matrix_elements.npy"), str(tmp_path / "rb_quadrupole_matrix_elements.npy")
+    a.saveMatrixElementTables(d, q)
+    rows = np.load(d)
+    assert rows.shape == (2, 7) and rows.dtype == np.float64
+    b = arc_b200.Rubidium()
+    assert b.loadMatrixElementTables(d, q) == 3
+    assert b._dipole == a._dipole and b._quadrupole == a._quadrupole
+    # element present in the memo: answered without any GPU call (no device in this test)
+    assert b.getRadialMatrixElement(60, 0, 0.5, 60, 1, 1.5) == 4131.5
+    assert b.getRadialMatrixElement(60, 1, 1.5, 60, 0, 0.5) == 4131.5
+    db = str(tmp_path / "precalculated_pair.db")
+    assert a.exportToArcDatabase(db) == (2, 1)
+    conn = sqlite3.connect(db)
+    c = conn.cursor()
+    # the reference's own lookup (alkali_atom_functions.py:1057-1062)
+    c.execute("SELECT dme FROM dipoleME WHERE n1= ? AND l1 = ? AND j1_x2 = ? AND n2 = ? AND l2 = ? AND j2_x2 = ?",
+              (60, 0, 1, 60, 1, 3))
+    assert c.fetchone()[0] == 4131.5
+    c.execute("SELECT qme FROM quadrupoleME WHERE n1= ? AND l1 = ? AND j1_x2 = ? AND n2 = ? AND l2 = ? AND j2_x2 = ?",
+              (60, 0, 1, 61, 2, 5))
+    assert c.fetchone()[0] == 1.25e6
+    conn.close()
+    e = arc_b200.Rubidium()
+    assert e.importFromArcDatabase(db) == 3 and e._dipole == a._dipole
+    sr = arc_b200.Strontium88()
+    sr._dipole[(60, 0, 0, 60, 1, 1, 0)] = 3000.0
+    db2 = str(tmp_path / "sr.db")
+    assert sr.exportToArcDatabase(db2) == (1, 0)
+    conn = sqlite3.connect(db2)
+    assert conn.execute("SELECT dme FROM dipoleME WHERE n1=60 AND l1=0 AND j1=0 AND n2=60 AND l2=1 AND j2=1 AND s=0").fetchone()[0] == 3000.0
+    conn.close()
