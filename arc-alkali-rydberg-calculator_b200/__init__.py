@@ -16,5 +16,6 @@ from .numerov import NumerovWavefunction, NumerovBack  # noqa: F401
 from .stark import StarkMap  # noqa: F401
 from .shirley import StarkBasisGenerator, ShirleyMethod  # noqa: F401
 from .pairstate import PairStateInteractions  # noqa: F401
+from .resonances import StarkMapResonances  # noqa: F401
 
 __version__ = "0.1.0"

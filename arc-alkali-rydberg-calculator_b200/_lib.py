@@ -56,6 +56,8 @@ _SIGNATURES = {
                                       c_i64]),
     "arcb200_floquet_sweep": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32,
                                       c_vp, c_vp, c_vp, c_vp, c_i64, c_i32]),
+    "arcb200_resonance_scan": (c_int, [c_int, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                       c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_dmma_peak": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "arcb200_sy2sb_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64]),
 }

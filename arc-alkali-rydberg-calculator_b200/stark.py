@@ -194,6 +194,29 @@ class StarkMap:
         self.composition = CompositionView(res.comp_c, res.comp_i)
         return
 
+    def _addState(self, n1, l1, j1, mj1):
+        """calculations_atom_single.py:1418-1430."""
+        from .pairstate import printStateStringLatex
+        if abs(self.s - 0.5) < 0.1:
+            return "|%s m_j=%d/2\\rangle" % (printStateStringLatex(n1, l1, j1), round(2 * mj1))
+        return "|%s m_j=%d\\rangle" % (printStateStringLatex(n1, l1, j1, s=self.s), round(mj1))
+
+    def _stateComposition(self, stateVector):
+        """LaTeX label of a [[coefficient, basis index], ...] list
+        (calculations_atom_single.py:1376-1393)."""
+        i = 0
+        totalContribution = 0
+        value = "$"
+        while (i < len(stateVector)) and (totalContribution < 0.95):
+            if i != 0 and stateVector[i][0] > 0:
+                value += "+"
+            value = value + ("%.2f" % stateVector[i][0]) + self._addState(*self.basisStates[stateVector[i][1]])
+            totalContribution += abs(stateVector[i][0]) ** 2
+            i += 1
+        if totalContribution < 0.999:
+            value += "+\\ldots"
+        return value + "$"
+
     def getPolarizability(self, maxField=1.0e10, showPlot=False, debugOutput=False,
                           minStateContribution=0.0):
         """calculations_atom_single.py:1432-1575 (fit of the tracked level to

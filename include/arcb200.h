@@ -154,6 +154,18 @@ int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_t dim0,
                           const double *d_F, int32_t idx0, double *d_y, double *d_hl,
                           double *d_tprob, void *d_work, int64_t work_bytes, int32_t batch);
 
+/* Pair-energy scan of StarkMapResonances.findResonances
+ * (calculations_atom_pairstate.py:4753-4789): keeps the pairs (j, jj) of single-atom Stark
+ * eigenstates of field i with eMin < y1[i][j] + y2[i][jj] - e0 < eMax and ok1[i][j] && ok2[i][jj],
+ * in the order of the reference's nested loops.  Two calls: d_rowoff == NULL counts the hits of
+ * every row (i, j) into d_rowcount[nF*N1]; with d_rowoff = exclusive prefix sum of those counts
+ * the hits are written to d_out_e / d_out_j / d_out_jj. */
+int arcb200_resonance_scan(int device, void *stream, int32_t nF, int32_t N1, int32_t N2,
+                           const double *d_y1, const double *d_y2, const uint8_t *d_ok1,
+                           const uint8_t *d_ok2, double e0, double eMin, double eMax,
+                           const int64_t *d_rowoff, int32_t *d_rowcount, double *d_out_e,
+                           int32_t *d_out_j, int32_t *d_out_jj);
+
 /* Pair-state sweep: for every distance R[p] (micrometres):
  *   H = diag(h0) + sum_o M_o / (R*1e-6)^(3+o)      (M_o dense N x N, o < norders)
  * d_M = DEVICE array of norders device pointers to the dense row-major M_o.

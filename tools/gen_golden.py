@@ -434,6 +434,29 @@ def gen_shirley(arc):
     np.savez_compressed(os.path.join(GOLD, "shirley_golden.npz"), **out)
 
 
+def gen_resonances(arc):
+    """StarkMapResonances.findResonances (calculations_atom_pairstate.py:4590-4790), small Rb
+    case: pair 30S1/2 30S1/2 -> dipole-coupled P-state pairs, 4 fields."""
+    from unittest.mock import MagicMock
+    import arc.calculations_atom_pairstate as cap
+    cap.plt.subplots.return_value = (MagicMock(), MagicMock())                            # fig, ax
+    rb = arc.Rubidium()
+    st1, st2 = [30, 0, 0.5, 0.5], [30, 0, 0.5, 0.5]
+    calc = arc.StarkMapResonances(rb, list(st1), rb, list(st2))
+    F = np.linspace(0, 600, 4)
+    t0 = time.time()
+    calc.findResonances(28, 32, 5, F, energyRange=[-20e9, 20e9])
+    out = dict(state1=np.array(st1), state2=np.array(st2), args=np.array([28, 32, 5], dtype=float), fields=F,
+               energyRange=np.array([-20e9, 20e9]), pairStateEnergy=calc.pairStateEnergy,
+               originalStateY=np.array(calc.originalStateY),
+               originalStateContribution=np.array(calc.originalStateContribution))
+    for i in range(len(F)):
+        out["y_%d" % i] = np.array(calc.y[i], dtype=float)
+        out["comp_%d" % i] = np.array(calc.composition[i]).astype(str) if len(calc.composition[i]) else np.zeros((0, 2), dtype=str)
+    np.savez_compressed(os.path.join(GOLD, "resonances_golden.npz"), **out)
+    print("resonances", [len(calc.y[i]) for i in range(len(F))], "%.1fs" % (time.time() - t0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -459,3 +482,5 @@ if __name__ == "__main__":
         gen_c6(arc)
     if "shirley" in what:
         gen_shirley(arc)
+    if "resonances" in what:
+        gen_resonances(arc)
