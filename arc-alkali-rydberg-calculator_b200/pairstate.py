@@ -629,3 +629,137 @@ class PairStateInteractions:
         self.y = [res.y[i] for i in range(len(self.r))]
         self.highlight = [res.hl[i] for i in range(len(self.r))]
         self.composition = PairCompositionView(self, res.comp_c, res.comp_i)
+
+    # ------------------------------------------------------------------ fit helpers
+    def _fit_range(self, rStart, rStop):
+        """calculations_atom_pairstate.py:4026-4043 (r is sorted descending by diagonalise)."""
+        fromRindex = -1
+        toRindex = -1
+        for br in range(len(self.r)):
+            if (fromRindex == -1) and (self.r[br] >= rStart):
+                fromRindex = br
+            if self.r[br] > rStop:
+                toRindex = br - 1
+                break
+        if (fromRindex != -1) and (toRindex == -1):
+            toRindex = len(self.r) - 1
+        if fromRindex == -1:
+            print("\nERROR: could not find data for energy levels for interatomic")
+            print("distances between %2.f and %.2f mu m.\n\n" % (rStart, rStop))
+        return fromRindex, toRindex
+
+    def getC6fromLevelDiagram(self, rStart, rStop, showPlot=False, minStateContribution=0.0):
+        """C6 (GHz um^6) from a fit of |E(R)| of the state that carries most of the original
+        pair state to log(C6/R^6 + offset) (calculations_atom_pairstate.py:3978-4112; plotting
+        is out of scope).  The argmax over `highlight` per distance is vectorised."""
+        from scipy.optimize import curve_fit
+        fromRindex, toRindex = self._fit_range(rStart, rStop)
+        if fromRindex == -1:
+            return 0
+        initialStateDetuning, initialStateDetuningX = [], []
+        for br in range(fromRindex, toRindex + 1):
+            hl = np.abs(np.asarray(self.highlight[br]))
+            index = int(np.argmax(hl)) if len(hl) else -1
+            if index != -1 and hl[index] > minStateContribution:
+                initialStateDetuning.append(abs(self.y[br][index]))
+                initialStateDetuningX.append(self.r[br])
+        initialStateDetuning = np.log(np.array(initialStateDetuning))
+        initialStateDetuningX = np.array(initialStateDetuningX)
+
+        def c6fit(r, c6, offset):
+            return np.log(c6 / r ** 6 + offset)
+        try:
+            popt, pcov = curve_fit(c6fit, initialStateDetuningX, initialStateDetuning, [1, 0])
+        except Exception as ex:
+            print(ex)
+            print("ERROR: unable to find a fit for C6.")
+            return False
+        print("c6 = ", popt[0], " GHz /R^6 (mu m)^6")
+        print("offset = ", popt[1])
+        self.fitX = initialStateDetuningX
+        self.fitY = initialStateDetuning
+        self.fittedCurveY = np.array([c6fit(v, popt[0], popt[1]) for v in initialStateDetuningX])
+        return popt[0]
+
+    def _adiabatic_branch(self, fromRindex, toRindex, minStateContribution, selectBranch):
+        """Track the original state from large to small R, stopping at a slope discontinuity
+        (calculations_atom_pairstate.py:4189-4216, 4356-4376)."""
+        det, detX = [], []
+        discontinuityDetected = False
+        for br in range(toRindex, fromRindex - 1, -1):
+            index = -1
+            maxPortion = minStateContribution
+            for br2 in range(len(self.y[br])):
+                if (abs(self.highlight[br][br2]) > maxPortion) and (
+                        not selectBranch or (self.y[br][br2] * selectBranch > 0.0)):
+                    index = br2
+                    maxPortion = abs(self.highlight[br][br2])
+            if len(detX) > 2:
+                slope1 = (det[-1] - det[-2]) / (detX[-1] - detX[-2])
+                slope2 = (abs(self.y[br][index]) - det[-1]) / (self.r[br] - detX[-1])
+                if abs(slope2) > 3.0 * abs(slope1):
+                    discontinuityDetected = True
+            if (index != -1) and (not discontinuityDetected):
+                det.append(abs(self.y[br][index]))
+                detX.append(self.r[br])
+        return det, detX
+
+    def getC3fromLevelDiagram(self, rStart, rStop, showPlot=False, minStateContribution=0.0,
+                              resonantBranch=+1):
+        """C3 (GHz um^3), fit to log(C3/R^3 + offset) (calculations_atom_pairstate.py:4114-4291;
+        like the reference the branch test multiplies by the boolean `selectBranch`)."""
+        from scipy.optimize import curve_fit
+        selectBranch = False
+        if abs(self.l - self.ll) == 1:
+            selectBranch = True
+            resonantBranch = float(resonantBranch)
+        fromRindex, toRindex = self._fit_range(rStart, rStop)
+        if fromRindex == -1:
+            return False
+        det, detX = self._adiabatic_branch(fromRindex, toRindex, minStateContribution, selectBranch)
+        det = np.log(np.array(det))
+        detX = np.array(detX)
+
+        def c3fit(r, c3, offset):
+            return np.log(c3 / r ** 3 + offset)
+        try:
+            popt, pcov = curve_fit(c3fit, detX, det, [1, 0])
+        except Exception as ex:
+            print(ex)
+            print("ERROR: unable to find a fit for C3.")
+            return False
+        print("c3 = ", popt[0], " GHz /R^3 (mu m)^3")
+        print("offset = ", popt[1])
+        self.fitX, self.fitY = detX, det
+        self.fittedCurveY = np.array([c3fit(v, popt[0], popt[1]) for v in detX])
+        return popt[0]
+
+    def getVdwFromLevelDiagram(self, rStart, rStop, showPlot=False, minStateContribution=0.0):
+        """van der Waals radius (um) (calculations_atom_pairstate.py:4293-4472)."""
+        from scipy.optimize import curve_fit
+        fromRindex, toRindex = self._fit_range(rStart, rStop)
+        if fromRindex == -1:
+            return False
+        det, detX = self._adiabatic_branch(fromRindex, toRindex, minStateContribution, False)
+        det = np.log(abs(np.array(det)))
+        detX = np.array(detX)
+
+        def vdwFit(r, offset, scale, vdw):
+            return np.log(abs(offset + scale * (1.0 - np.sqrt(1.0 + (vdw / r) ** 6))
+                              / (1.0 - np.sqrt(1 + vdw ** 6))))
+        noOfPoints = len(detX)
+        print("Data points to fit = ", noOfPoints)
+        try:
+            popt, pcov = curve_fit(vdwFit, detX, det, [0, det[noOfPoints // 2], detX[noOfPoints // 2]])
+        except Exception as ex:
+            print(ex)
+            print("ERROR: unable to find a fit for van der Waals distance.")
+            return False
+        if (detX[0] < popt[2]) or (popt[2] < detX[-1]):
+            print("WARNING: vdw radius seems to be outside the fitting range!")
+            print("It's estimated to be around %.2f mu m from the current fit." % popt[2])
+        print("Rvdw =  ", popt[2], " mu m")
+        print("offset = ", popt[0], "\n scale = ", popt[1])
+        self.fitX, self.fitY = detX, det
+        self.fittedCurveY = np.array([vdwFit(v, popt[0], popt[1], popt[2]) for v in detX])
+        return popt[2]

@@ -130,3 +130,29 @@ def test_pair_sort_eigenvectors_matches_reference(gold_dir):
     # unsorted run returns ascending rows; the sorted run generally does not
     calc.diagonalise(g["r"], int(g["k"]))
     assert np.all(np.diff(np.array(calc.y), axis=1) >= 0)
+
+
+def test_level_diagram_fits_against_reference(gold_dir):
+    """getC6fromLevelDiagram / getVdwFromLevelDiagram / getC3fromLevelDiagram
+    (calculations_atom_pairstate.py:3978-4472; "C6 extraction" of BASELINE configs[2]) on the
+    GPU level diagrams against values frozen from the live reference."""
+    import json
+    import arc_b200
+    g = json.load(open(os.path.join(gold_dir, "levelfit_golden.json")))
+    rb = arc_b200.Rubidium()
+    c = g["c6"]
+    p = arc_b200.PairStateInteractions(rb, *c["ctor"])
+    p.defineBasis(*c["basis"])
+    assert len(p.basisStates) == c["N"]
+    p.diagonalise(np.linspace(*c["R"][:2], int(c["R"][2])), c["k"])
+    c6 = p.getC6fromLevelDiagram(*c["range"])
+    assert abs(c6 / c["C6"] - 1) <= 1e-5, (c6, c["C6"])
+    rv = p.getVdwFromLevelDiagram(3.0, 9.5, minStateContribution=0.5)
+    assert abs(rv / c["Rvdw"] - 1) <= 1e-3, (rv, c["Rvdw"])
+    c = g["c3"]
+    p = arc_b200.PairStateInteractions(rb, *c["ctor"])
+    p.defineBasis(*c["basis"])
+    assert len(p.basisStates) == c["N"]
+    p.diagonalise(np.linspace(*c["R"][:2], int(c["R"][2])), c["k"])
+    c3 = p.getC3fromLevelDiagram(*c["range"], resonantBranch=+1)
+    assert abs(c3 / c["C3"] - 1) <= 1e-5, (c3, c["C3"])

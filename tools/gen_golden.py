@@ -457,6 +457,37 @@ def gen_resonances(arc):
     print("resonances", [len(calc.y[i]) for i in range(len(F))], "%.1fs" % (time.time() - t0))
 
 
+def gen_levelfit(arc):
+    """getC6fromLevelDiagram / getC3fromLevelDiagram / getVdwFromLevelDiagram
+    (calculations_atom_pairstate.py:3978-4472) on small Rb pair bases."""
+    import json as _json
+    import arc.calculations_atom_pairstate as cap
+    from unittest.mock import MagicMock
+    cap.plt.subplots.return_value = (MagicMock(), MagicMock())
+    rb = arc.Rubidium()
+    out = {}
+    # off-resonant S+S pair: van der Waals (C6) regime
+    p = arc.PairStateInteractions(rb, 60, 0, 0.5, 60, 0, 0.5, 0.5, 0.5)
+    p.defineBasis(0., 0., 2, 2, 15e9)
+    R = np.linspace(3.0, 10.0, 36)
+    p.diagonalise(R, 40)
+    out["c6"] = {"ctor": [60, 0, .5, 60, 0, .5, .5, .5], "basis": [0., 0., 2, 2, 15e9], "R": [3.0, 10.0, 36], "k": 40,
+                 "N": len(p.basisStates), "range": [4.0, 9.5],
+                 "C6": float(p.getC6fromLevelDiagram(4.0, 9.5)),
+                 "Rvdw": float(p.getVdwFromLevelDiagram(3.0, 9.5, minStateContribution=0.5))}
+    # resonant S+P pair: C3 regime
+    p = arc.PairStateInteractions(rb, 60, 0, 0.5, 60, 1, 1.5, 0.5, 0.5)
+    p.defineBasis(0., 0., 1, 1, 10e9)
+    R = np.linspace(2.0, 12.0, 30)
+    p.diagonalise(R, 20)
+    out["c3"] = {"ctor": [60, 0, .5, 60, 1, 1.5, .5, .5], "basis": [0., 0., 1, 1, 10e9], "R": [2.0, 12.0, 30], "k": 20,
+                 "N": len(p.basisStates), "range": [3.0, 11.0],
+                 "C3": float(p.getC3fromLevelDiagram(3.0, 11.0, resonantBranch=+1))}
+    with open(os.path.join(GOLD, "levelfit_golden.json"), "w") as f:
+        _json.dump(out, f, indent=1)
+    print("levelfit", out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["radial", "angular", "stark", "pair", "divalent"]
     arc = refenv.load(home_name="home_golden_" + "_".join(what))
@@ -484,3 +515,5 @@ if __name__ == "__main__":
         gen_shirley(arc)
     if "resonances" in what:
         gen_resonances(arc)
+    if "levelfit" in what:
+        gen_levelfit(arc)
