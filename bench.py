@@ -164,7 +164,9 @@ def bench_c3(args, rank, world):
     npts = args.points
     allR = np.linspace(1.0, 10.0, 1000)
     # weak scaling: every rank sweeps `npts` R points of the 1-10 um range (its own shard)
-    myR = np.sort(np.resize(allR[rank::max(world, 1)], npts))[::-1].copy()
+    # (interleaved subsets of the 1000-point grid that each span the whole 1-10 um range)
+    pick = (np.linspace(0, 999 - (max(world, 1) - 1), npts).astype(int) + rank) % 1000
+    myR = np.sort(allR[pick])[::-1].copy()
     ops = calc.device_operators()
     launches = [0]
 
@@ -202,6 +204,16 @@ def bench_c3(args, rank, world):
     finally:
         sw.dist_info = old
     e2e_value = npts * world * args.steps / (ms_e2e * 1e-3)
+    # the use the configuration names ("C6 extraction"): fit of the tracked level of the last
+    # end-to-end sweep (host post-pass, calculations_atom_pairstate.py:3978-4112)
+    c6_fit = None
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            c6_fit = float(calc.getC6fromLevelDiagram(4.0, 9.0))
+    except Exception:
+        c6_fit = None
 
     # roofline of the dominant kernel: time it alone on one batch
     hbm, hbm_src = measured_peaks()
@@ -279,7 +291,7 @@ def bench_c3(args, rank, world):
     del d_A, work
     out = {"value": value, "ms": ms, "e2e_value": e2e_value, "ms_e2e": ms_e2e, "h2d": h2d, "d2h": d2h,
            "launches": launches[0], "roofline": roof, "clocks": clk.summary(), "N": N, "k": k,
-           "t_defineBasis_s": t_define, "batch": batch, "calc": calc, "R": myR}
+           "t_defineBasis_s": t_define, "batch": batch, "calc": calc, "R": myR, "c6_fit": c6_fit}
     return out
 
 
@@ -465,6 +477,69 @@ def bench_shirley(args):
                              "sample": "2 of the 100 points: numpy.linalg.eigh + transition probabilities"}}
 
 
+def bench_c4(args):
+    """BASELINE.json configs[3]: Sr88 divalent StarkMap, singlet (s=0) and triplet (s=1) bases,
+    n=50-70, l<=30; a bounded number of the 2000 fields per GPU."""
+    import torch
+    import arc_b200
+    out = {}
+    nF = 148
+    for name, j, s_ in (("singlet", 0, 0), ("triplet", 1, 1)):
+        calc = arc_b200.StarkMap(arc_b200.Strontium88())
+        t0 = time.perf_counter()
+        calc.defineBasis(60, 0, j, 0, 50, 70, 30, s=s_)
+        t_def = time.perf_counter() - t0
+        F = np.linspace(0, 200, 2000)[:: 2000 // nF][:nF]
+        ts = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            calc.diagonalise(F)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        sec = float(np.mean(ts[1:]))
+        i = nF // 2
+        t0 = time.perf_counter()
+        w = np.linalg.eigh(calc.mat1 + calc.mat2 * F[i])[0]
+        dt = time.perf_counter() - t0
+        out[name] = {"N": len(calc.basisStates), "value": nF / sec, "unit": "solves/s", "fields": nF,
+                     "s_per_sweep_e2e": sec, "defineBasis_s": t_def,
+                     "max_rel_err_vs_cpu_sample": float(np.abs(calc.y[i] - w).max() / np.abs(w).max()),
+                     "cpu_baseline": {"value": 1.0 / dt, "unit": "solves/s", "cores": "default BLAS threads",
+                                      "kind": "port", "sample": "1 field: numpy.linalg.eigh"}}
+    return {"workload": "c4: Sr88 StarkMap defineBasis(60,0,J,0,50,70,30,s=S), %d of 2000 fields 0-200 V/m" % nF,
+            "metric": "fp64_eigensolves_per_sec", **out}
+
+
+def bench_c5(args):
+    """BASELINE.json configs[4]: Rb 80D5/2+80D5/2, theta=pi/4, Bz=1e-4 T, N=10384; 18 of the 4096
+    R points (one batch of the one-stage cluster-per-matrix solver), k=250."""
+    import torch
+    import arc_b200
+    t0 = time.perf_counter()
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 80, 2, 2.5, 80, 2, 2.5, 2.5, 2.5)
+    calc.defineBasis(np.pi / 4, 0, 3, 4, 10e9, Bz=1e-4)
+    t_def = time.perf_counter() - t0
+    N = len(calc.basisStates)
+    R = np.linspace(2, 20, 4096)[:: 4096 // 18][:18]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    calc.diagonalise(R, 250)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    H = calc.matDiagonal.toarray() + calc.matR[0].toarray() / (calc.r[0] * 1e-6) ** 3
+    t0 = time.perf_counter()
+    w = np.linalg.eigvalsh(H)
+    dt = time.perf_counter() - t0
+    sel = np.sort(np.argsort(np.abs(w), kind="stable")[:250])
+    return {"workload": "c5: Rb 80D5/2+80D5/2 theta=pi/4 Bz=1e-4 T, N=%d, 18 of 4096 R points, k=250" % N,
+            "metric": "fp64_eigensolves_per_sec", "value": 18 / sec, "unit": "solves/s", "s_per_point": sec / 18,
+            "defineBasis_s": t_def, "gpu_launches": calc.last_sweep.kernel_launches,
+            "max_rel_err_vs_cpu_sample": float(np.abs(calc.y[0] - w[sel]).max() / np.abs(w).max()),
+            "cpu_baseline": {"value": 1.0 / dt, "unit": "solves/s", "cores": "default BLAS threads", "kind": "port",
+                             "sample": "1 R point: numpy.linalg.eigvalsh of the dense matrix (eigenvalues only)"}}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -553,6 +628,14 @@ def main():
                 sub["shirley_doc"] = bench_shirley(args)
             except Exception as ex:
                 sub["shirley_doc"] = {"error": repr(ex)}
+            try:
+                sub["stark_c4"] = bench_c4(args)
+            except Exception as ex:
+                sub["stark_c4"] = {"error": repr(ex)}
+            try:
+                sub["pair_c5"] = bench_c5(args)
+            except Exception as ex:
+                sub["pair_c5"] = {"error": repr(ex)}
     barrier(world)
     if rank == 0:
         line = {
@@ -572,6 +655,7 @@ def main():
             "gpu_launches": r["launches"] * args.steps,
             "roofline": r["roofline"], "cpu_baseline": cpu, "clocks": r["clocks"],
             "defineBasis_s": r["t_defineBasis_s"],
+            "c6_from_level_diagram_GHz_um6": r["c6_fit"],
             "sub": sub,
         }
         print(json.dumps(line))
