@@ -93,5 +93,7 @@ int eig_pick_cluster(int N, int nmat);
 // bulge-chasing reflectors in oV2/oTau2; back-transformation Z = Q1 (Q2 Z)
 int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
 int eig_sb2st(const EigSlots &S, int nmat, cudaStream_t st, int *launches);
+// (with_q1: also apply the band-reduction reflectors Q1 on the row-major window, i.e. the whole
+// back-transformation Z = Q1 (Q2 Z); otherwise eig_ormtr has to follow)
 int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
-                 int *launches);
+                 int *launches, bool with_q1);

@@ -9,6 +9,7 @@
 //   epilogue  y, highlight and the top-k composition per eigenvector, so eigenvectors
 //             never leave the GPU (calculations_atom_single.py:988-1021, 1395-1416;
 //             calculations_atom_pairstate.py:3494-3520).
+#include <stdlib.h>
 #include "eig.cuh"
 
 namespace {
@@ -308,8 +309,10 @@ int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma
     if (rc) return rc;
     const int32_t *sel = window ? W.sel0 : nullptr;
     if (L.two_stage) {
-        rc = eig_q2_apply(W.S, nmat, sel, nsel, st, launches);
-        if (rc) return rc;
+        const char *ev = getenv("ARCB200_ORMTR_T");         // tuning knob: 0 = slab kernel for Q1
+        const bool fused = !(ev && ev[0] == '0');
+        rc = eig_q2_apply(W.S, nmat, sel, nsel, st, launches, fused);
+        if (rc || fused) return rc;
     }
     return eig_ormtr(W.S, nmat, sel, nsel, st, launches);
 }

@@ -1062,6 +1062,197 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, 2) q2_kernel(TsArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// back-transformation with the band-reduction reflectors, on the row-major eigenvector window
+// ------------------------------------------------------------------------------------------
+// Zt <- Q1 Zt, Q1 = prod_p (I - V_p T_p V_p^T), panels last to first (LAPACK dormtr 'L','N').
+// One CTA per (matrix, group of 256 eigenvector columns); warp <-> 32 columns.  The 32x32 chunk of
+// V_p is staged ONCE per CTA and step in shared memory and shared by the 8 warps (the one-stage
+// kernel keeps an 8-column slab resident and re-reads V from L2 for every slab: 64 passes over V
+// per matrix at k = 250); every warp streams its own 32x32 chunk of Zt through a transit tile.
+//   pass 1   W = V_p^T Zt      (accumulated over the row chunks, DMMA)
+//            W <- -T_p W       (DMMA, through shared memory for the operand layout)
+//   pass 2   Zt += V_p W       (per chunk, DMMA, written back with 128-bit stores)
+constexpr int OT2_PITCH = 36;
+__global__ void __launch_bounds__(256, 1) ormtr_t_kernel(TsArgs a)
+{
+    constexpr int PT = OT2_PITCH;
+    const int mat = blockIdx.y;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int np = a.Npad, lda = a.Npad, NB = a.NB;
+    const size_t kp = (size_t)a.kp;
+    const int c0 = 256 * blockIdx.x + 32 * wid;
+    const bool act = c0 < a.kp;
+    double *slot = a.base + (size_t)mat * a.slot;
+    const double *__restrict__ A = slot + a.oA;
+    const double *__restrict__ Tfac = slot + a.oTfac;
+    double *Zt = slot + a.oZt;
+
+    extern __shared__ double sm[];
+    double(*Vs)[32 * PT] = reinterpret_cast<double(*)[32 * PT]>(sm);        // [buf][row k][col j]
+    double *Ts = sm + 2 * 32 * PT;                                          // [j][l]
+    double *Tz = sm + 3 * 32 * PT + wid * (2 * 32 * PT);                    // per warp: Z chunk [row][col]
+    double *Wt = Tz + 32 * PT;                                              // per warp: W [j][col]
+
+    // V chunk ch of panel p -> Vs[buf]: element (row rr, reflector cc); the first chunk carries the
+    // implicit unit diagonal and the zeros above it (the stored entries there belong to R)
+    auto stageV = [&](int buf, int p, int ch) {
+        const int r0 = 32 * (p + 1) + 32 * ch;
+        const int rr = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = (tid >> 5) + 8 * q;
+            double x = A[(size_t)(r0 + rr) + (size_t)(32 * p + cc) * lda];
+            if (ch == 0) x = (rr < cc) ? 0.0 : ((rr == cc) ? 1.0 : x);
+            Vs[buf][rr * PT + cc] = x;
+        }
+    };
+    // this warp's 32x32 chunk of Zt (rows r0.., columns c0..) -> Tz, 16-byte pieces
+    auto issueZ = [&](int r0) {
+        const double *src = Zt + (size_t)(r0 + (lane >> 4)) * kp + c0 + (lane & 15) * 2;
+        double *dst = Tz + (lane >> 4) * PT + (lane & 15) * 2;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            cp_async16_t(dst, src);
+            src += 2 * kp;
+            dst += 2 * PT;
+        }
+    };
+
+    for (int p = NB - 2; p >= 0; --p) {
+        const int m0 = 32 * (p + 1), nch = NB - (p + 1);
+        __syncthreads();
+        for (int t = tid; t < 1024; t += 256) Ts[(t >> 5) * PT + (t & 31)] = Tfac[(size_t)p * 1024 + t];
+        // ---------------------------------------------------------------- pass 1: W = V^T Z
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        stageV(0, p, 0);
+        if (act) issueZ(m0);
+        cp_async_wait_all_t();
+        __syncthreads();
+        for (int ch = 0; ch < nch; ++ch) {
+            const int buf = ch & 1;
+            double fb[4][8];
+            if (act) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) fb[y][ks] = Tz[(4 * ks + tig) * PT + 8 * y + grp];
+            }
+            __syncwarp();
+            if (ch + 1 < nch) {
+                if (act) issueZ(m0 + 32 * (ch + 1));
+                stageV(buf ^ 1, p, ch + 1);
+            }
+            if (act) {
+                const double *va = Vs[buf] + tig * PT + grp;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double fa[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) fa[x] = va[4 * ks * PT + 8 * x];     // V^T: (m = j, k = row)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], fb[y][ks]);
+                }
+            }
+            cp_async_wait_all_t();
+            __syncthreads();
+        }
+        // ---------------------------------------------------------------- W <- -T W
+        if (act) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) Wt[(8 * x + grp) * PT + 8 * y + 2 * tig + h] = acc[x][y][h];
+            __syncwarp();
+            double w2[4][4][2];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) w2[x][y][0] = w2[x][y][1] = 0.0;
+            const double *ta = Ts + grp * PT + tig;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double fa[4], fw[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) fa[x] = ta[8 * x * PT + 4 * ks];            // T (m = j, k = l)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) fw[y] = Wt[(4 * ks + tig) * PT + 8 * y + grp];
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) dmma_t(w2[x][y][0], w2[x][y][1], fa[x], fw[y]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) Wt[(8 * x + grp) * PT + 8 * y + 2 * tig + h] = -w2[x][y][h];
+            __syncwarp();
+        }
+        // ---------------------------------------------------------------- pass 2: Z += V W
+        __syncthreads();
+        stageV(0, p, 0);
+        if (act) issueZ(m0);
+        cp_async_wait_all_t();
+        __syncthreads();
+        for (int ch = 0; ch < nch; ++ch) {
+            const int buf = ch & 1;
+            const int r0 = m0 + 32 * ch;
+            double c[4][4][2];
+            if (act) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double2 q = *reinterpret_cast<const double2 *>(Tz + (8 * x + grp) * PT + 8 * y + 2 * tig);
+                        c[x][y][0] = q.x;
+                        c[x][y][1] = q.y;
+                    }
+            }
+            __syncwarp();
+            if (ch + 1 < nch) {
+                if (act) issueZ(r0 + 32);
+                stageV(buf ^ 1, p, ch + 1);
+            }
+            if (act) {
+                const double *va = Vs[buf] + grp * PT + tig;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double fa[4], fw[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) fa[x] = va[8 * x * PT + 4 * ks];        // V (m = row, k = j)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) fw[y] = Wt[(4 * ks + tig) * PT + 8 * y + grp];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(c[x][y][0], c[x][y][1], fa[x], fw[y]);
+                }
+                double *zo = Zt + (size_t)(r0 + grp) * kp + c0 + 2 * tig;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        *reinterpret_cast<double2 *>(zo + (size_t)(8 * x) * kp + 8 * y) = make_double2(c[x][y][0], c[x][y][1]);
+            }
+            cp_async_wait_all_t();
+            __syncthreads();
+        }
+    }
+}
+
+
 TsArgs make_args(const EigSlots &S)
 {
     const EigLayout &L = S.L;
@@ -1117,7 +1308,7 @@ int eig_sb2st(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 }
 
 int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
-                 int *launches)
+                 int *launches, bool with_q1)
 {
     if (S.L.N < 3 || nsel <= 0) return 0;
     TsArgs a = make_args(S);
@@ -1128,8 +1319,16 @@ int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, c
     zt_in_kernel<<<dim3(rowtiles, coltiles, nmat), 256, 0, st>>>(a);
     const int nslab = a.kp / 32;
     q2_kernel<<<dim3((nslab + Q2_WARPS - 1) / Q2_WARPS, nmat), Q2_WARPS * 32, 0, st>>>(a);
+    int nl = 3;
+    if (with_q1 && S.L.NB >= 2) {
+        // Q1 on the same row-major window (T factors were left in oTfac by the band reduction)
+        const size_t smem = (size_t)(3 * 32 * OT2_PITCH + TS_WARPS * 2 * 32 * OT2_PITCH) * sizeof(double);
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ormtr_t_kernel<<<dim3((a.kp + 255) / 256, nmat), 256, smem, st>>>(a);
+        ++nl;
+    }
     zt_out_kernel<<<dim3(S.L.NB, coltiles, nmat), 256, 0, st>>>(a);
     ARCB200_LAUNCH_CHECK("q2 kernels");
-    if (launches) *launches += 3;
+    if (launches) *launches += nl;
     return 0;
 }
