@@ -123,3 +123,41 @@ def test_stark_sweep_in_two_stage_window():
         gaps = np.diff(w0) > 1e-7 * scale
         cid = np.concatenate([[0], np.cumsum(gaps)])
         assert np.abs(np.bincount(cid, weights=r.hl[f]) - np.bincount(cid, weights=hl0)).max() <= 1e-6
+
+
+def test_pair_sweep_window_in_two_stage_window():
+    """k nearest sigma (ascending) through arcb200_pair_sweep with N in the default two-stage
+    range: windowed D&C -> Q2 on the row-major window -> Q1 (ormtr_t), k not a multiple of 32,
+    sigma != 0, several distances, against numpy.linalg.eigh (calculations_atom_pairstate.py:3444)."""
+    from arc_b200 import sweep
+    rng = np.random.default_rng(21)
+    N = 1090
+    h0 = rng.standard_normal(N) * 3
+    M = rng.standard_normal((N, N)) * 1e-18 * (rng.random((N, N)) < 0.05)
+    M = np.triu(M, 1)
+    M = M + M.T
+    r, c = np.nonzero(M)
+    ops = sweep.PairOperators(h0, [(r, c, M[r, c])], N)
+    R = np.array([6.0, 2.5, 1.2])
+    for k, sigma in ((37, 0.0), (250, 0.9)):
+        res = sweep.pair_sweep(ops, R, k, sigma, opi=17, distributed=False)
+        for i, rv in enumerate(R):
+            H = np.diag(h0) + M / (rv * 1e-6) ** 3
+            w, v = np.linalg.eigh(H)
+            scale = np.abs(w).max()
+            sel = np.sort(np.argsort(np.abs(w - sigma), kind="stable")[:k])
+            assert np.abs(res.y[i] - w[sel]).max() <= 1e-9 * scale
+            gaps = np.diff(w[sel]) > 1e-7 * scale
+            cid = np.concatenate([[0], np.cumsum(gaps)])
+            a = np.bincount(cid, weights=res.hl[i])
+            b = np.bincount(cid, weights=v[17, sel] ** 2)
+            assert np.abs(a - b).max() <= 1e-6
+
+
+def test_window_edges_of_the_two_stage_range():
+    """N = 1024 (first size on the two-stage path) and a ragged N just above it."""
+    from arc_b200 import sweep
+    for N in (1024, 1027):
+        A = _sym(np.random.default_rng(N), 1, N)
+        w, Z = sweep.syevd_batched(A)
+        _check_eig(A, w, Z)
