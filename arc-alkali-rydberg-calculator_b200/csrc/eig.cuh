@@ -24,9 +24,8 @@ constexpr int EIG_LDB = 72;         // leading dimension of the compact lower ba
 
 static inline size_t eig_align(size_t x) { return (x + 31) & ~(size_t)31; }
 
-// Two-stage tridiagonalisation (dense -> band -> tridiagonal) for mid-sized matrices that are
-// solved one CTA per matrix; small matrices are latency bound either way and very large ones
-// need a whole cluster per matrix (one-stage kernel).  ARCB200_TWO_STAGE=0/1 overrides.
+// Two-stage tridiagonalisation (dense -> band -> tridiagonal) for N >= 1024; smaller matrices
+// are latency bound either way and use the one-stage kernel.  ARCB200_TWO_STAGE=0/1 overrides.
 int eig_use_two_stage(int N);
 
 static inline EigLayout eig_layout(int N, int nvec)

@@ -24,53 +24,10 @@
 //                  column, so a reflector is 32 uniform loads + 64 FMAs per lane with no cross-lane
 //                  traffic; a 39-row register window slides over 32 consecutive sweeps.
 // Index conventions and application orders are modelled in tools/proto_two_stage.py.
-#include <stdlib.h>
-#include "eig.cuh"
-
-#ifdef TS_PROFILE
-#define TSP_DECL long long tsp_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tsp_last = clock64();
-#define TSP(k) { long long now_ = clock64(); tsp_t[k] += now_ - tsp_last; tsp_last = now_; }
-#else
-#define TSP_DECL
-#define TSP(k)
-#endif
+#include "eig_twostage.cuh"
 
 namespace {
-
-constexpr int TS_THREADS = 256;
-constexpr int TS_WARPS = 8;
-constexpr int BSTR = 36;          // [n][k] operand tiles: conflict-free DMMA fragment reads
-
-struct TsArgs {
-    int N, Npad, NB;
-    double *base;
-    size_t slot;
-    size_t oA, oWp, oVp, oTau, oTfac, oBand, oV2, oTau2, oD, oE, oZ, oZt;
-    int nsel, kp;
-    const int32_t *sel0;
-};
-
-__device__ __forceinline__ void dmma_t(double &d0, double &d1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async8_t(void *dst, const void *src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src));
-}
-__device__ __forceinline__ void cp_async16_t(void *dst, const void *src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
-}
-__device__ __forceinline__ void cp_async_wait_all_t()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+using namespace ts;
 
 // ------------------------------------------------------------------------------------------
 // stage 1: dense -> band
@@ -1272,13 +1229,18 @@ int eig_use_two_stage(int N)
 {
     const char *ev = getenv("ARCB200_TWO_STAGE");
     if (ev) return ev[0] == '1' && N >= 96;
-    return N >= 1024 && N <= 4096;
+    return N >= 1024 && N <= 16384;
 }
 
 int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 {
     if (!S.L.two_stage) { arcb200_set_error("sy2sb: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
+    // one CTA per matrix needs about as many matrices as SMs; smaller batches (large N) spread
+    // every matrix over many CTAs with one launch per phase and panel
+    const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
+    const bool multi = em ? (em[0] == '1') : (nmat < 74);
+    if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
     const int warps = ev ? atoi(ev) : 8;
     if (warps == 4) {

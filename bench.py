@@ -229,7 +229,7 @@ def bench_c3(args, rank, world):
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     del A
-    two_stage = os.environ.get("ARCB200_TWO_STAGE", "1") != "0" and 1024 <= N <= 4096
+    two_stage = os.environ.get("ARCB200_TWO_STAGE", "1") != "0" and 1024 <= N <= 16384
 
     def timed(fn, reps=3):
         for _ in range(2):
