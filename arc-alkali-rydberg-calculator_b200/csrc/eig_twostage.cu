@@ -916,8 +916,10 @@ __global__ void __launch_bounds__(256) zt_out_kernel(TsArgs a)
 // The 8 warps of a CTA walk the same (group, step) sequence of one matrix: the 32 reflectors of
 // the next block (8 KB) and their taus are prefetched into registers while the current block is
 // applied from shared memory (broadcast reads), one __syncthreads per block.
-constexpr int Q2_WARPS = 4;
-__global__ void __launch_bounds__(Q2_WARPS * 32, 2) q2_kernel(TsArgs a)
+// Q2_WARPS warps (slabs) per CTA (one warp per CTA was measured slower: nothing hides the
+// staging latency)
+template <int Q2_WARPS>
+__global__ void __launch_bounds__(Q2_WARPS * 32, Q2_WARPS == 4 ? 2 : 1) q2_kernel(TsArgs a)
 {
     __shared__ __align__(16) double Vs[2][32][32];
     __shared__ double taus[2][32];
@@ -1031,7 +1033,9 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, 2) q2_kernel(TsArgs a)
 //            W <- -T_p W       (DMMA, through shared memory for the operand layout)
 //   pass 2   Zt += V_p W       (per chunk, DMMA, written back with 128-bit stores)
 constexpr int OT2_PITCH = 36;
-__global__ void __launch_bounds__(256, 1) ormtr_t_kernel(TsArgs a)
+// OTW warps per CTA (8: one CTA covers 256 columns; 4: two CTAs per 256 columns for small batches)
+template <int OTW>
+__global__ void __launch_bounds__(OTW * 32, 1) ormtr_t_kernel(TsArgs a)
 {
     constexpr int PT = OT2_PITCH;
     const int mat = blockIdx.y;
@@ -1039,7 +1043,7 @@ __global__ void __launch_bounds__(256, 1) ormtr_t_kernel(TsArgs a)
     const int grp = lane >> 2, tig = lane & 3;
     const int np = a.Npad, lda = a.Npad, NB = a.NB;
     const size_t kp = (size_t)a.kp;
-    const int c0 = 256 * blockIdx.x + 32 * wid;
+    const int c0 = 32 * OTW * blockIdx.x + 32 * wid;
     const bool act = c0 < a.kp;
     double *slot = a.base + (size_t)mat * a.slot;
     const double *__restrict__ A = slot + a.oA;
@@ -1058,8 +1062,7 @@ __global__ void __launch_bounds__(256, 1) ormtr_t_kernel(TsArgs a)
         const int r0 = 32 * (p + 1) + 32 * ch;
         const int rr = tid & 31;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int cc = (tid >> 5) + 8 * q;
+        for (int cc = tid >> 5; cc < 32; cc += OTW) {
             double x = A[(size_t)(r0 + rr) + (size_t)(32 * p + cc) * lda];
             if (ch == 0) x = (rr < cc) ? 0.0 : ((rr == cc) ? 1.0 : x);
             Vs[buf][rr * PT + cc] = x;
@@ -1080,7 +1083,7 @@ __global__ void __launch_bounds__(256, 1) ormtr_t_kernel(TsArgs a)
     for (int p = NB - 2; p >= 0; --p) {
         const int m0 = 32 * (p + 1), nch = NB - (p + 1);
         __syncthreads();
-        for (int t = tid; t < 1024; t += 256) Ts[(t >> 5) * PT + (t & 31)] = Tfac[(size_t)p * 1024 + t];
+        for (int t = tid; t < 1024; t += OTW * 32) Ts[(t >> 5) * PT + (t & 31)] = Tfac[(size_t)p * 1024 + t];
         // ---------------------------------------------------------------- pass 1: W = V^T Z
         double acc[4][4][2];
 #pragma unroll
@@ -1280,13 +1283,19 @@ int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, c
     const int rowtiles = (S.L.Npad + 64) / 32, coltiles = a.kp / 32;
     zt_in_kernel<<<dim3(rowtiles, coltiles, nmat), 256, 0, st>>>(a);
     const int nslab = a.kp / 32;
-    q2_kernel<<<dim3((nslab + Q2_WARPS - 1) / Q2_WARPS, nmat), Q2_WARPS * 32, 0, st>>>(a);
+    q2_kernel<4><<<dim3((nslab + 3) / 4, nmat), 128, 0, st>>>(a);
     int nl = 3;
     if (with_q1 && S.L.NB >= 2) {
         // Q1 on the same row-major window (T factors were left in oTfac by the band reduction)
-        const size_t smem = (size_t)(3 * 32 * OT2_PITCH + TS_WARPS * 2 * 32 * OT2_PITCH) * sizeof(double);
-        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ormtr_t_kernel<<<dim3((a.kp + 255) / 256, nmat), 256, smem, st>>>(a);
+        if ((long long)nmat * ((a.kp + 255) / 256) < 148) {
+            const size_t smem = (size_t)(3 * 32 * OT2_PITCH + 4 * 2 * 32 * OT2_PITCH) * sizeof(double);
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_t_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ormtr_t_kernel<4><<<dim3((a.kp + 127) / 128, nmat), 128, smem, st>>>(a);
+        } else {
+            const size_t smem = (size_t)(3 * 32 * OT2_PITCH + 8 * 2 * 32 * OT2_PITCH) * sizeof(double);
+            ARCB200_CUDA_CHECK(cudaFuncSetAttribute(ormtr_t_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ormtr_t_kernel<8><<<dim3((a.kp + 255) / 256, nmat), 256, smem, st>>>(a);
+        }
         ++nl;
     }
     zt_out_kernel<<<dim3(S.L.NB, coltiles, nmat), 256, 0, st>>>(a);

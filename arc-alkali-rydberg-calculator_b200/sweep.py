@@ -56,10 +56,13 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     free, _total = torch.cuda.mem_get_info(device)
     lib = _lib.load()
     per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
-    b = int(min(npoints, max(1, (0.6 * free) // per)))
+    # large matrices: the kernels that give a matrix one CTA (bulge chasing, panel QR, Q2) cost
+    # the same for any batch below the SM count, so take as many as the memory holds
+    frac = 0.8 if N > 4096 else 0.6
+    b = int(min(npoints, max(1, (frac * free) // per)))
     # one CTA (or a small cluster) per matrix: 148 matrices in flight fill the GPU
     # (two per SM while two CTAs' shared memory fits, N <= ~4000)
-    cap = 592 if N <= 512 else (296 if N <= 4000 else (148 if N <= 4096 else 18))
+    cap = 592 if N <= 512 else (296 if N <= 4000 else 148)
     b = max(1, min(b, cap))
     # equal chunks: a nearly empty tail pass costs a full sweep latency
     nchunks = -(-npoints // b)
