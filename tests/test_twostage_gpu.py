@@ -38,13 +38,24 @@ def _check_eig(A, w, Z, tol=1e-10):
         assert np.abs(Z[b].T @ Z[b] - np.eye(N)).max() <= tol
 
 
+@pytest.mark.parametrize("multi", ["0", "1"])
 @pytest.mark.parametrize("N", [97, 128, 200, 333])
-def test_small_matrices_forced(force_two_stage, N):
-    """Ragged sizes (N not a multiple of the band width, single trailing blocks)."""
+def test_small_matrices_forced(force_two_stage, N, multi):
+    """Ragged sizes (N not a multiple of the band width, single trailing blocks), through both
+    band-reduction kernels: one CTA per matrix (sy2sb_kernel) and per-phase launches with many
+    CTAs per matrix (eig_sy2sb_multi.cu, the default for small batches)."""
     from arc_b200 import sweep
-    A = _sym(np.random.default_rng(N), 3, N)
-    w, Z = sweep.syevd_batched(A)
-    _check_eig(A, w, Z)
+    old = os.environ.get("ARCB200_SY2SB_MULTI")
+    os.environ["ARCB200_SY2SB_MULTI"] = multi
+    try:
+        A = _sym(np.random.default_rng(N), 3, N)
+        w, Z = sweep.syevd_batched(A)
+        _check_eig(A, w, Z)
+    finally:
+        if old is None:
+            del os.environ["ARCB200_SY2SB_MULTI"]
+        else:
+            os.environ["ARCB200_SY2SB_MULTI"] = old
 
 
 def test_band_stage_preserves_spectrum(force_two_stage):
