@@ -53,8 +53,12 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
         batch = int(os.environ["ARCB200_BATCH"])
     if batch is not None:
         return max(1, min(int(batch), npoints))
-    torch.cuda.empty_cache()          # cached blocks of earlier sweeps would shrink the batch
     free, _total = torch.cuda.mem_get_info(device)
+    # blocks cached by torch from earlier sweeps are reusable: count them as free
+    try:
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    except Exception:
+        pass
     lib = _lib.load()
     per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
     # large matrices: the kernels that give a matrix one CTA (bulge chasing, panel QR, Q2) cost
