@@ -583,7 +583,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (Rb 60S+60S pair Hamiltonian built from quantum defects; no dataset)",
-            "config": {"workload": "c3: Rb 60S1/2+60S1/2 PairStateInteractions dn=5 dl=5 dEmax=25GHz, N=2363, k=250",
+            "config": {"workload": "c3: Rb 60S1/2+60S1/2 PairStateInteractions dn=5 dl=5 dEmax=25GHz (BASELINE configs[2]), "
+                                   "N=2363, k=250 eigenpairs nearest the pair state per R point",
                        "points_per_step": nR},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": procs, "kind": "port",
                              "sample": "%d R points per step, scipy eigsh shift-invert k=250, %d processes x 1 BLAS thread"
