@@ -54,11 +54,14 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     if batch is not None:
         return max(1, min(int(batch), npoints))
     free, _total = torch.cuda.mem_get_info(device)
-    # blocks cached by torch from earlier sweeps are reusable: count them as free
+    # blocks cached by torch from earlier sweeps are reusable: count them as free ...
+    cached = 0
     try:
-        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
     except Exception:
         pass
+    free_now = free
+    free += cached
     lib = _lib.load()
     per = max(1, lib.arcb200_sweep_workspace_bytes(N, 1, nvec))
     # large matrices: the kernels that give a matrix one CTA (bulge chasing, panel QR, Q2) cost
@@ -71,7 +74,11 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     b = max(1, min(b, cap))
     # equal chunks: a nearly empty tail pass costs a full sweep latency
     nchunks = -(-npoints // b)
-    return -(-npoints // nchunks)
+    b = -(-npoints // nchunks)
+    # ... and hand them back to the driver first when the workspace does not fit beside them
+    if cached and per * b > 0.9 * free_now:
+        torch.cuda.empty_cache()
+    return b
 
 
 class SweepResult:
