@@ -28,6 +28,10 @@ import time
 
 import numpy as np
 
+# the sub-workloads allocate workspaces of very different sizes (68 GB for C3, 141 GB for C5):
+# expandable segments let torch hand freed memory back instead of pinning whole segments
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -523,14 +527,18 @@ def bench_c4(args):
 def bench_c5(args):
     """BASELINE.json configs[4]: Rb 80D5/2+80D5/2, theta=pi/4, Bz=1e-4 T, N=10384; 32 of the 4096
     R points (one batch: 4.4 GB of workspace per matrix), k=250."""
+    import gc
     import torch
     import arc_b200
+    gc.collect()
+    torch.cuda.empty_cache()
     t0 = time.perf_counter()
     calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 80, 2, 2.5, 80, 2, 2.5, 2.5, 2.5)
     calc.defineBasis(np.pi / 4, 0, 3, 4, 10e9, Bz=1e-4)
     t_def = time.perf_counter() - t0
     N = len(calc.basisStates)
     R = np.linspace(2, 20, 4096)[:: 4096 // 32][:32]
+    calc.diagonalise(R, 250)              # warm-up: maps the 141 GB workspace
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     calc.diagonalise(R, 250)
