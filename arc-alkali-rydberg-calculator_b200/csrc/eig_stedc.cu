@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(PREP_THREADS) merge_prep_kernel(DcArgs a, int 
     const int tid = threadIdx.x;
     __shared__ double sred[PREP_THREADS];
     __shared__ int s_k, s_nrot, s_ndef;
-    __shared__ double s_tol, s_rho;
 
     // z = [last row of Q1-block ; +-first row of Q2-block] / sqrt(2)
     const double sgn = (rho_in < 0.0) ? -1.0 : 1.0;
@@ -234,7 +233,6 @@ __global__ void __launch_bounds__(PREP_THREADS) merge_prep_kernel(DcArgs a, int 
     dmax = sred[0];
     const double rho = fabs(2.0 * rho_in);
     const double tol = 8.0 * EPS * fmax(dmax, zmax);
-    if (tid == 0) { s_tol = tol; s_rho = rho; }
 
     // merge the two ascending runs: rank by binary search
     for (int j = tid; j < n; j += PREP_THREADS) {
@@ -598,8 +596,6 @@ __global__ void __launch_bounds__(256) merge_finish_kernel(DcArgs a, int level, 
     double *aux = slot + a.oAux;
     double *lam = slot + a.oLam;
     const double *lamnew = aux + (size_t)AX_LAMNEW * ld + s;
-    const int32_t *defsrc = islot + a.oPerm + (size_t)IX_DEFSRC * ld + s + k;
-    const int32_t *defpos = islot + a.oPerm + (size_t)IX_DEFPOS * ld + s;
     if (threadIdx.x == 0) {
         GemmProblem P;
         P.A = Qold + s;                    // rows s..s+n
@@ -626,7 +622,6 @@ __global__ void __launch_bounds__(256) merge_finish_kernel(DcArgs a, int level, 
         probs[blockIdx.x] = P;
     }
     for (int j = threadIdx.x; j < n; j += blockDim.x) lam[s + j] = lamnew[j];
-    (void)defsrc; (void)defpos;
 }
 
 // deflated eigenvectors are plain column copies Qold(:, src) -> Qnew(:, s + pos); one warp

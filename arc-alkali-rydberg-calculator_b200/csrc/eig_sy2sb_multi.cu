@@ -37,11 +37,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, in
     double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + UNI);
     double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
     double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
-    double(*red)[WARPS][32] = reinterpret_cast<double(*)[WARPS][32]>(sm + UNI + 3 * 1056);   // [par][warp][j]
-    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 2 * WARPS * 32);  // [warp][j]
-    double(*hrow)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32); // [par][j]
-    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 64); // [par][warp], [par][15] = alpha
-    double *taus = sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 96;                       // [32]
+    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056);          // [par][j]
+    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 64);   // [par][warp], [par][15] = alpha
+    double *taus = sm + UNI + 3 * 1056 + 96;                                         // [32]
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int grp = lane >> 2, tig = lane & 3;
@@ -510,7 +508,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, in
                 if (work) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
                         const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
                         const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
                         const double fv[4] = {va.x, va.y, vb.x, vb.y};
@@ -566,7 +563,7 @@ __global__ void __launch_bounds__(256) band_extract_kernel(TsArgs a)
 int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launches)
 {
     constexpr int W = 8;
-    const size_t smem = (2 * W * 32 * 36 + 4608 + 3 * 1056 + 3 * W * 32 + 128) * sizeof(double);
+    const size_t smem = (2 * W * 32 * 36 + 4608 + 3 * 1056 + 128) * sizeof(double);
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

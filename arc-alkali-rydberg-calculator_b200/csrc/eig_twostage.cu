@@ -56,11 +56,9 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
     double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + UNI);
     double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
     double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
-    double(*red)[WARPS][32] = reinterpret_cast<double(*)[WARPS][32]>(sm + UNI + 3 * 1056);   // [par][warp][j]
-    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 2 * WARPS * 32);  // [warp][j]
-    double(*hrow)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32); // [par][j]
-    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 64); // [par][warp], [par][15] = alpha
-    double *taus = sm + UNI + 3 * 1056 + 3 * WARPS * 32 + 96;                       // [32]
+    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056);          // [par][j]
+    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 64);   // [par][warp], [par][15] = alpha
+    double *taus = sm + UNI + 3 * 1056 + 96;                                         // [32]
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int grp = lane >> 2, tig = lane & 3;
@@ -530,7 +528,6 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
                 if (work) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
                         const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
                         const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
                         const double fv[4] = {va.x, va.y, vb.x, vb.y};
@@ -1041,7 +1038,7 @@ __global__ void __launch_bounds__(OTW * 32, 1) ormtr_t_kernel(TsArgs a)
     const int mat = blockIdx.y;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int grp = lane >> 2, tig = lane & 3;
-    const int np = a.Npad, lda = a.Npad, NB = a.NB;
+    const int lda = a.Npad, NB = a.NB;
     const size_t kp = (size_t)a.kp;
     const int c0 = 32 * OTW * blockIdx.x + 32 * wid;
     const bool act = c0 < a.kp;
@@ -1247,11 +1244,11 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
     const int warps = ev ? atoi(ev) : 8;
     if (warps == 4) {
-        const size_t smem = (2 * 4 * 32 * 36 + 4608 + 3 * 1056 + 3 * 4 * 32 + 128) * sizeof(double);
+        const size_t smem = (2 * 4 * 32 * 36 + 4608 + 3 * 1056 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<4><<<nmat, 128, smem, st>>>(a);
     } else {
-        const size_t smem = (2 * 8 * 32 * 36 + 4608 + 3 * 1056 + 3 * 8 * 32 + 128) * sizeof(double);
+        const size_t smem = (2 * 8 * 32 * 36 + 4608 + 3 * 1056 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<8><<<nmat, 256, smem, st>>>(a);
     }
