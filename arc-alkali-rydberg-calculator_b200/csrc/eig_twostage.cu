@@ -21,8 +21,14 @@
 //                  transposed halves of the products go through a padded shared-memory tile.
 //                  All reflectors of sweep s are stored contiguously in V2[s+1:, s].
 //   q2_kernel      Z <- Q2 Z on a row-major copy of the selected eigenvectors: lane <-> eigenvector
-//                  column, so a reflector is 32 uniform loads + 64 FMAs per lane with no cross-lane
-//                  traffic; a 39-row register window slides over 32 consecutive sweeps.
+//                  column, so a reflector is 64 FMAs per lane with no cross-lane traffic; a 39-row
+//                  register window slides over 32 consecutive sweeps; the 32 reflectors of the
+//                  next block are staged in shared memory while the current block is applied.
+//   ormtr_t_kernel Z <- Q1 Z on the same row-major window (compact-WY panels, DMMA): the chunk of
+//                  V is staged once per CTA and step and shared by all warps, each warp streams
+//                  its 32 columns of Z through a transit tile.
+// For small batches (large N) the band reduction runs as one launch per phase and panel with many
+// CTAs per matrix (eig_sy2sb_multi.cu, same phase bodies).
 // Index conventions and application orders are modelled in tools/proto_two_stage.py.
 #include "eig_twostage.cuh"
 
