@@ -33,7 +33,7 @@ _SIGNATURES = {
     "arcb200_device_info": (c_int, [c_int, c_vp]),
     "arcb200_numerov_lengths": (c_i64, [c_i32, c_vp, c_vp]),
     "arcb200_numerov_batch": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                      c_vp, c_vp, c_i32]),
+                                      c_vp, c_vp, c_i32, c_vp]),
     "arcb200_radial_integrals": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_vp]),
     "arcb200_radial_gram": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -43,23 +43,24 @@ _SIGNATURES = {
     "arcb200_sweep_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "arcb200_stark_sweep": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32,
                                     c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                    c_i64, c_i32]),
+                                    c_i64, c_i32, c_vp]),
     "arcb200_pair_sweep": (c_int, [c_int, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp,
                                    c_i32, c_dbl, c_i32, c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp,
-                                   c_vp, c_vp, c_vp, c_i64, c_i32]),
+                                   c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "arcb200_scatter_coo": (c_int, [c_int, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_syevd_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
-                                      c_i64]),
+                                      c_i64, c_vp]),
     "arcb200_sytrd_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                      c_i64, c_i32]),
+                                      c_i64, c_i32, c_vp]),
     "arcb200_stedc_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                      c_i64]),
+                                      c_i64, c_vp]),
     "arcb200_floquet_sweep": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32,
-                                      c_vp, c_vp, c_vp, c_vp, c_i64, c_i32]),
+                                      c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "arcb200_resonance_scan": (c_int, [c_int, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                                        c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_dmma_peak": (c_int, [c_int, c_vp, c_vp, c_vp]),
-    "arcb200_sy2sb_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64]),
+    "arcb200_dfma_peak": (c_int, [c_int, c_vp, c_vp, c_vp]),
+    "arcb200_sy2sb_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 
 
@@ -85,17 +86,33 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.arcb200_abi_version() != 1:
+        if lib.arcb200_abi_version() != 2:
             raise ArcB200Error("libarcb200 ABI version mismatch")
         _lib = lib
     return _lib
 
 
 def check(rc, what):
-    if rc < 0:
+    """0 = success; anything else is an error (include/arcb200.h)."""
+    if rc != 0:
         raise ArcB200Error("%s failed (%d): %s"
                            % (what, rc, load().arcb200_last_error().decode()))
     return rc
+
+
+class LaunchCount:
+    """Host int32 for the trailing `h_launches` out-parameter of the sweep entry points."""
+
+    def __init__(self):
+        self._v = ctypes.c_int32(0)
+
+    @property
+    def addr(self):
+        return ctypes.addressof(self._v)
+
+    @property
+    def value(self):
+        return int(self._v.value)
 
 
 _dev_checked = set()

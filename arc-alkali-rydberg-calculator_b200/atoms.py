@@ -58,6 +58,11 @@ class AlkaliAtom:
         self.a1, self.a2, self.a3, self.a4, self.rc = a["a1"], a["a2"], a["a3"], a["a4"], a["rc"]
         self.gS, self.gL = a["gS"], a["gL"]
         self.groundStateN = a["groundStateN"]
+        # tuples, exactly like the reference (alkali_atom_data.py:286-295).  The reference's
+        # consumers test `[n, l, j] in atom.extraLevels` with a LIST (calculations_atom_single.py:
+        # 749-751, calculations_atom_pairstate.py:824-829), which never equals a tuple, so states
+        # below groundStateN are always dropped from Stark / pair bases.  Parity keeps that
+        # (pinned by tests/golden/stark_*_lown_golden.npz from the live reference).
         self.extraLevels = [tuple(x) for x in a["extraLevels"]]
         self.minQuantumDefectN = a["minQuantumDefectN"]
         self.NISTdataLevels = a["NISTdataLevels"]
@@ -85,9 +90,10 @@ class AlkaliAtom:
         # cancelling elements (|value| < 1e-4 sqrt(<r^p>_a <r^p>_b)) by up to 3e-12 of that scale.
         # Default off: the one-warp-per-pair kernel reproduces the reference's formula exactly.
         self.fast_radial = False
-        # shard_radial=True (opt-in, collective): tables of >= 1024 new elements are sharded over
-        # the ranks of the default torch.distributed group and all-gathered (radial.sharded_table)
-        self.shard_radial = False
+        # radial_group (opt-in, collective): tables of >= 1024 new elements are sharded over the
+        # ranks of this torch.distributed group (sweep.WORLD = the default group) and all-gathered
+        # (radial.sharded_table); None = every process computes its own table, no collective
+        self.radial_group = None
         self.gram_threshold = 64
 
     # pickling support (saveCalculation, alkali_atom_functions.py:4136-4278): plain data only
@@ -252,9 +258,9 @@ class AlkaliAtom:
                 pair_rows[t, slot] = index[st]
             pair_rows[t, 2] = power
         rb = _radial.RadialBatch(np.array(states), normalise=True, device=self.device)
-        if getattr(self, "shard_radial", False) and len(todo) >= 1024:
-            # collective: every rank of the default process group builds the same table
-            vals = rb.integrals_sharded(pair_rows).cpu().numpy()
+        if getattr(self, "radial_group", None) is not None and len(todo) >= 1024:
+            # collective: every rank of the group builds the same table
+            vals = rb.integrals_sharded(pair_rows, self.radial_group).cpu().numpy()
         elif not self.fast_radial or len(todo) < self.gram_threshold:
             vals = rb.integrals(pair_rows)               # one warp per pair
         else:

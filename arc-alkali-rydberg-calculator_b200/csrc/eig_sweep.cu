@@ -26,7 +26,7 @@ size_t work_bytes(const EigLayout &L, int batch)
     b += (size_t)batch * L.slot_ints * sizeof(int32_t);
     b += (size_t)batch * EIG_MAX_NODES * EIG_PROB_BYTES;
     b += (size_t)batch * sizeof(int32_t) + 256;
-    return b;
+    return (b + 255) & ~(size_t)255;          // whatever follows the workspace stays 256-byte aligned
 }
 
 WorkView carve(void *d_work, const EigLayout &L, int batch)
@@ -214,6 +214,85 @@ __global__ void __launch_bounds__(256) epilogue_kernel(
         for (int t = kk; t < topk; ++t) { comp_c[orow * topk + t] = 0.0; comp_i[orow * topk + t] = -1; }
 }
 
+// topk > MAXTOP (upTo = -1 or upTo > 9 in the reference's _stateComposition2,
+// calculations_atom_single.py:1399-1407): the whole eigenvector sorted by |c| descending.
+// One CTA per eigenvector: bitonic sort of (|c|, index) keys in shared memory (N padded to a
+// power of two), then the first topk entries are written while the running sum of c^2 is below
+// contrib_max (the reference's loop condition; upTo = -1 passes contrib_max = 2 = no cut).
+// Ties in |c| are ordered by ascending index (numpy's heapsort leaves them unspecified).
+__global__ void __launch_bounds__(256) full_composition_kernel(
+    int N, int Npad, int P2, const double *base, size_t slot, size_t oQ,
+    const int32_t *__restrict__ sel0, int nsel, int topk, double contrib_max,
+    double *__restrict__ comp_c, int32_t *__restrict__ comp_i, int point0)
+{
+    extern __shared__ double fc_sm[];
+    double *key = fc_sm;                                   // [P2]
+    int32_t *idx = reinterpret_cast<int32_t *>(fc_sm + P2);   // [P2]
+    __shared__ double part[256];
+    const int mat = blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
+    const int s0 = sel0 ? sel0[mat] : 0;
+    const double *q = base + (size_t)mat * slot + oQ + (size_t)(s0 + i) * Npad;
+    const size_t orow = (size_t)(point0 + mat) * nsel + i;
+    for (int t = tid; t < P2; t += 256) {
+        key[t] = (t < N) ? fabs(q[t]) : -1.0;
+        idx[t] = (t < N) ? t : 0x7fffffff;
+    }
+    __syncthreads();
+    // descending by key, ascending by index on ties
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P2; t += 256) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const double a = key[t], b = key[u];
+                    const int ia = idx[t], ib = idx[u];
+                    const bool a_first = (a > b) || (a == b && ia < ib);   // a belongs before b
+                    const bool up = ((t & k) == 0);
+                    if (up != a_first) { key[t] = b; key[u] = a; idx[t] = ib; idx[u] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // exclusive prefix sums of c^2 in sorted order (chunk per thread, then across threads)
+    const int chunk = (N + 255) / 256;
+    const int lo = min(N, tid * chunk), hi = min(N, lo + chunk);
+    double s = 0.0;
+    for (int t = lo; t < hi; ++t) s += key[t] * key[t];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double run = 0.0;
+        for (int t = 0; t < 256; ++t) { const double v = part[t]; part[t] = run; run += v; }
+    }
+    __syncthreads();
+    double run = part[tid];
+    for (int t = lo; t < hi; ++t) {
+        if (t < topk) {
+            const bool valid = run < contrib_max;
+            comp_c[orow * topk + t] = valid ? q[idx[t]] : 0.0;
+            comp_i[orow * topk + t] = valid ? idx[t] : -1;
+        }
+        run += key[t] * key[t];
+    }
+    for (int t = N + tid; t < topk; t += 256) { comp_c[orow * topk + t] = 0.0; comp_i[orow * topk + t] = -1; }
+}
+
+static int launch_full_composition(int N, int Npad, const double *base, size_t slot, size_t oQ,
+                                   const int32_t *sel0, int nsel, int nmat, int topk, double contrib_max,
+                                   double *comp_c, int32_t *comp_i, int point0, cudaStream_t st)
+{
+    int P2 = 1;
+    while (P2 < N) P2 <<= 1;
+    const size_t smem = (size_t)P2 * (sizeof(double) + sizeof(int32_t));
+    if (smem > 200 * 1024) { arcb200_set_error("full composition: N=%d too large", N); return -1; }
+    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(full_composition_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    full_composition_kernel<<<dim3(nsel, nmat), 256, smem, st>>>(N, Npad, P2, base, slot, oQ, sel0, nsel, topk,
+                                                                 contrib_max, comp_c, comp_i, point0);
+    return 0;
+}
+
 // ---------------------------------------------------------------- adiabatic overlaps
 // O[t][i][j] = ( v_t,i . v_(t-1),j )^2 between the selected eigenvectors of consecutive sweep
 // points (calculations_atom_pairstate.py:3462-3468).  One CTA per 16x16 output tile.
@@ -341,10 +420,10 @@ static int stark_sweep_impl(int device, void *stream, int32_t N, const double *d
                             const double *d_drive_w, int32_t topk, double contrib_max,
                             double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
                             void *d_work, int64_t wbytes, int32_t batch, int32_t dim0,
-                            double *d_tprob)
+                            double *d_tprob, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     if (nF <= 0) return 0;
-    if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -362,8 +441,14 @@ static int stark_sweep_impl(int device, void *stream, int32_t N, const double *d
         if (rc) return rc;
         epilogue_kernel<<<dim3((N + 7) / 8, nmat), 256, 0, st>>>(
             N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, nullptr, N, idx0, d_drive_w,
-            topk > 0 ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, f0);
+            (topk > 0 && topk <= MAXTOP) ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, f0);
         ++launches;
+        if (topk > MAXTOP) {
+            rc = launch_full_composition(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, nullptr, N, nmat, topk,
+                                         contrib_max, d_comp_c, d_comp_i, f0, st);
+            if (rc) return rc;
+            ++launches;
+        }
         if (d_tprob) {
             transprob_kernel<<<dim3((N + 255) / 256, nmat), 256, 0, st>>>(
                 N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, dim0, d_hl, d_tprob, f0);
@@ -371,28 +456,30 @@ static int stark_sweep_impl(int device, void *stream, int32_t N, const double *d
         }
     }
     ARCB200_LAUNCH_CHECK("stark sweep");
-    return launches;
+    if (h_launches) *h_launches = launches;
+    return 0;
 }
 
 extern "C" int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
                                    const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
                                    const double *d_drive_w, int32_t topk, double contrib_max,
                                    double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
-                                   void *d_work, int64_t wbytes, int32_t batch)
+                                   void *d_work, int64_t wbytes, int32_t batch, int32_t *h_launches)
 {
     return stark_sweep_impl(device, stream, N, d_h0diag, d_V, nF, d_F, idx0, d_drive_w, topk,
                             contrib_max, d_y, d_hl, d_comp_c, d_comp_i, d_work, wbytes, batch, 0,
-                            nullptr);
+                            nullptr, h_launches);
 }
 
 extern "C" int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_t dim0,
                                      const double *d_h0diag, const double *d_B, int32_t nF,
                                      const double *d_F, int32_t idx0, double *d_y, double *d_hl,
-                                     double *d_tprob, void *d_work, int64_t wbytes, int32_t batch)
+                                     double *d_tprob, void *d_work, int64_t wbytes, int32_t batch,
+                                     int32_t *h_launches)
 {
     if (dim0 <= 0 || N % dim0 != 0) { arcb200_set_error("floquet_sweep: N must be a multiple of dim0"); return -1; }
     return stark_sweep_impl(device, stream, N, d_h0diag, d_B, nF, d_F, idx0, nullptr, 0, 2.0, d_y,
-                            d_hl, nullptr, nullptr, d_work, wbytes, batch, dim0, d_tprob);
+                            d_hl, nullptr, nullptr, d_work, wbytes, batch, dim0, d_tprob, h_launches);
 }
 
 extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0diag,
@@ -401,10 +488,10 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
                                   const double *d_drive_w, int32_t topk, double contrib_max,
                                   double *d_y, double *d_hl, double *d_comp_c,
                                   int32_t *d_comp_i, double *d_overlap, void *d_work,
-                                  int64_t wbytes, int32_t batch)
+                                  int64_t wbytes, int32_t batch, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     if (nR <= 0) return 0;
-    if (topk > MAXTOP) { arcb200_set_error("topk > %d not supported", MAXTOP); return -1; }
     if (k < 1 || k > N) { arcb200_set_error("k must be in [1, N]"); return -1; }
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -413,8 +500,10 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
     const WorkView W = carve(d_work, L, batch);
     const int ntiles = L.NB * (L.NB + 1) / 2;
     int launches = 0;
-    // eigenvector window of the last point of the previous batch (for the overlaps)
-    double *prevZ = (double *)((char *)d_work + work_bytes(L, batch));
+    // eigenvector window of the last point of the previous batch (for the overlaps): right after
+    // the carved workspace, 256-byte aligned like the carve itself (work_bytes() is a multiple of
+    // 256 and already contains the slack of the alignment of d_work)
+    double *prevZ = (double *)((((uintptr_t)d_work + 255) & ~(uintptr_t)255) + work_bytes(L, batch) - 256);
     if (d_overlap && (int64_t)(work_bytes(L, batch) + (size_t)N * k * sizeof(double)) > wbytes) {
         arcb200_set_error("workspace too small for overlaps (add N*k doubles)");
         return -1;
@@ -427,9 +516,15 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
         int rc = solve_batch(W, nmat, k, true, sigma, st, &launches);
         if (rc) return rc;
         epilogue_kernel<<<dim3((k + 7) / 8, nmat), 256, 0, st>>>(
-            N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w, topk,
-            contrib_max, d_y, d_hl, d_comp_c, d_comp_i, p0);
+            N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w,
+            topk <= MAXTOP ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, p0);
         ++launches;
+        if (topk > MAXTOP) {
+            rc = launch_full_composition(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, nmat, topk,
+                                         contrib_max, d_comp_c, d_comp_i, p0, st);
+            if (rc) return rc;
+            ++launches;
+        }
         if (d_overlap) {
             overlap_kernel<<<dim3((k + 15) / 16, (k + 15) / 16, nmat), 256, 0, st>>>(
                 N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, p0 == 0 ? nullptr : prevZ,
@@ -440,13 +535,15 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
         }
     }
     ARCB200_LAUNCH_CHECK("pair sweep");
-    return launches;
+    if (h_launches) *h_launches = launches;
+    return 0;
 }
 
 extern "C" int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_t batch,
                                      double *d_A, double *d_w, double *d_Z, void *d_work,
-                                     int64_t wbytes)
+                                     int64_t wbytes, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     if (batch <= 0) return 0;
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -460,7 +557,8 @@ extern "C" int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_
     store_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1,
                                                          L.oLam, d_Z, d_w);
     ARCB200_LAUNCH_CHECK("syevd");
-    return launches + 2;
+    if (h_launches) *h_launches = launches + 2;
+    return 0;
 }
 
 // ---------------------------------------------------------------- stage-level entry points
@@ -479,8 +577,9 @@ __global__ void put_vec_kernel(int N, double *base, size_t slot, size_t off, con
 
 extern "C" int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
                                      const double *d_A, double *d_d, double *d_e, double *d_tau,
-                                     void *d_work, int64_t wbytes, int32_t cluster)
+                                     void *d_work, int64_t wbytes, int32_t cluster, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -501,7 +600,8 @@ extern "C" int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_
     copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oE, d_e);
     if (d_tau) copy_vec_kernel<<<dim3(4, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oTau, d_tau);
     ARCB200_LAUNCH_CHECK("sytrd_batched");
-    return launches + 3;
+    if (h_launches) *h_launches = launches + 3;
+    return 0;
 }
 
 // band after stage 1 of the two-stage reduction: d_band[b][j][d] = B[j+d][j], d = 0..32
@@ -517,8 +617,9 @@ __global__ void copy_band_kernel(int N, const double *base, size_t slot, size_t 
 
 extern "C" int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_t batch,
                                      const double *d_A, double *d_band, void *d_work,
-                                     int64_t wbytes)
+                                     int64_t wbytes, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -531,13 +632,15 @@ extern "C" int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_
     if (rc) return rc;
     copy_band_kernel<<<dim3(16, batch), 256, 0, st>>>(N, W.S.dbl, L.slot_doubles, L.oBand, d_band);
     ARCB200_LAUNCH_CHECK("sy2sb_batched");
-    return launches + 2;
+    if (h_launches) *h_launches = launches + 2;
+    return 0;
 }
 
 extern "C" int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
                                      const double *d_d, const double *d_e, double *d_w,
-                                     double *d_Q, void *d_work, int64_t wbytes)
+                                     double *d_Q, void *d_work, int64_t wbytes, int32_t *h_launches)
 {
+    if (h_launches) *h_launches = 0;
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -551,5 +654,6 @@ extern "C" int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_
     store_dense_kernel<<<dim3(148, batch), 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1,
                                                          L.oLam, d_Q, d_w);
     ARCB200_LAUNCH_CHECK("stedc_batched");
-    return launches + 3;
+    if (h_launches) *h_launches = launches + 3;
+    return 0;
 }

@@ -179,5 +179,5 @@ extern "C" int arcb200_radial_gram(int device, void *stream, int32_t nblocks,
     gram_fix_kernel<<<dim3((max_rows * max_cols + 255) / 256, nblocks), 256, 0, st>>>(
         blk, d_rows, d_cols, d_states, d_offsets, d_psi, d_rgrid, Lgrid, d_out);
     ARCB200_LAUNCH_CHECK("radial gram kernels");
-    return 3;
+    return 0;   // 3 kernels launched
 }

@@ -67,5 +67,5 @@ extern "C" int arcb200_resonance_scan(int device, void *stream, int32_t nF, int3
         nF, N1, N2, d_y1, d_y2, d_ok1, d_ok2, e0, eMin, eMax, d_rowoff, d_rowcount, d_out_e, d_out_j,
         d_out_jj);
     ARCB200_LAUNCH_CHECK("resonance_scan_kernel");
-    return 1;
+    return 0;
 }

@@ -152,7 +152,9 @@ class PairStateInteractions:
                       - self._E1(n, l, j) - self._E2(nn, ll, jj))
 
     def _w6j(self, l, s, j, j1, c, l1):
-        if self.reference_6j_table_quirk and (l1 - l) == 2:
+        # the table is only consulted for l, l1 <= wignerPrecalJmax = 23 (wigner.py:306-315);
+        # beyond it the reference evaluates the true (non-zero) 6j
+        if self.reference_6j_table_quirk and (l1 - l) == 2 and l <= 23 and l1 <= 23:
             return 0.0
         return Wigner6j(l, s, j, j1, c, l1)
 
@@ -443,10 +445,10 @@ class PairStateInteractions:
             limitBasisToMj, progressOutput=progressOutput, debugOutput=debugOutput)
         nch = len(self.channel)
         opi = 0
-        self.index = np.zeros(nch + 1, dtype=np.int16)
+        index = np.zeros(nch + 1, dtype=np.int64)   # cast to the reference's int16 after the size check
         prod_idx = []           # per channel: index of each basis state in the full m1 x m2 product
         for i, ch in enumerate(self.channel):
-            self.index[i] = len(self.basisStates)
+            index[i] = len(self.basisStates)
             pidx = []
             ja, jb = ch[2], ch[5]
             for m1c in np.linspace(ja, -ja, round(1 + 2 * ja)):
@@ -461,10 +463,11 @@ class PairStateInteractions:
                                 and abs(ch[5] - self.jj) < 0.1 and abs(m2c - self.m2) < 0.1):
                             opi = len(self.basisStates) - 1
             prod_idx.append(np.array(pidx, dtype=np.int64))
-        self.index[-1] = len(self.basisStates)
+        index[-1] = len(self.basisStates)
         dimension = len(self.basisStates)
         if dimension > 32767:
             raise ValueError("basis too large (the reference's index array is int16)")
+        self.index = index.astype(np.int16)
 
         # ---- matDiagonal (calculations_atom_pairstate.py:3133-3159)
         diag = np.zeros(dimension)
@@ -584,8 +587,10 @@ class PairStateInteractions:
 
     def diagonalise(self, rangeR, noOfEigenvectors, drivingFromState=[0, 0, 0, 0, 0],
                     eigenstateDetuning=0.0, sortEigenvectors=False, progressOutput=False,
-                    debugOutput=False, batch=None):
-        """calculations_atom_pairstate.py:3246-3522."""
+                    debugOutput=False, batch=None, group=None):
+        """calculations_atom_pairstate.py:3246-3522.  `group` (extension): None = all R points
+        on this GPU; sweep.WORLD or a torch.distributed group = points sharded over its ranks
+        (collective call, every rank gets the full result)."""
         self.r = np.sort(rangeR)[::-1]
         dimension = len(self.basisStates)
         self.noOfEigenvectors = noOfEigenvectors
@@ -621,7 +626,8 @@ class PairStateInteractions:
         ops = self.device_operators()
         res = _sweep.pair_sweep(ops, self.r, noOfEigenvectors, eigenstateDetuning * 1.0e-9,
                                 self.originalPairStateIndex, drive_w=drive_w, topk=4,
-                                contrib_max=0.95, batch=batch, want_overlap=bool(sortEigenvectors))
+                                contrib_max=0.95, batch=batch, want_overlap=bool(sortEigenvectors),
+                                group=group)
         self.last_sweep = res
         self.gpu_kernel_launches += res.kernel_launches
         if sortEigenvectors:

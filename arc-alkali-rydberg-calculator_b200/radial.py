@@ -27,7 +27,7 @@ def make_state(innerLimit, outerLimit, step, init1, init2, l, s, j, stateEnergy,
     return rec
 
 
-def sharded_table(compute, pairs, group=None):
+def sharded_table(compute, pairs, group="world"):
     """One matrix-element table for all ranks of the process group: rank g evaluates the
     contiguous shard pairs[g*P/G:(g+1)*P/G] with `compute(shard) -> tensor[len(shard)]` and
     the shards are all-gathered once (NCCL over NVLink on GPUs, gloo in the CPU tests), so the
@@ -54,7 +54,8 @@ class RadialBatch:
         self.offsets = np.zeros(n + 1, dtype=np.int64)
         total = lib.arcb200_numerov_lengths(n, self.states.ctypes.data,
                                             self.offsets.ctypes.data)
-        _lib.check(total, "arcb200_numerov_lengths")
+        if total < 0:
+            _lib.check(int(total), "arcb200_numerov_lengths")
         self.total = int(total)
         self.lengths = self.states["length"].copy()
         dev = torch.device("cuda", self.device)
@@ -66,13 +67,33 @@ class RadialBatch:
         self.d_r = torch.empty(self.total + 64, dtype=torch.float64, device=dev)
         self.d_norm = torch.empty(n, dtype=torch.float64, device=dev)
         self.d_dp = torch.empty(n, dtype=torch.int32, device=dev)
+        self.d_status = torch.zeros(n, dtype=torch.int32, device=dev)
         rc = lib.arcb200_numerov_batch(
             self.device, _lib.stream_ptr(self.device), n, _lib.ptr(self.d_states),
             _lib.ptr(self.d_offsets), _lib.ptr(self.d_order), _lib.ptr(self.d_psi),
             _lib.ptr(self.d_r), _lib.ptr(self.d_norm), _lib.ptr(self.d_dp),
-            1 if normalise else 0)
+            1 if normalise else 0, _lib.ptr(self.d_status))
         _lib.check(rc, "arcb200_numerov_batch")
         self.kernel_launches = 1
+        self._status = None
+
+    def status(self):
+        """Per-state status of the integration (0 ok, 1 the reference's "Numerov error",
+        2 no usable norm); one device -> host copy, cached."""
+        if self._status is None:
+            self._status = self.d_status.cpu().numpy()
+        return self._status
+
+    def raise_on_failure(self):
+        """The reference's C extension returns NULL for a failed state (arc_c_extensions.c:200);
+        the drop-in raises RuntimeError naming the states (SURVEY 8b seam B1)."""
+        st = self.status()
+        bad = np.nonzero(st)[0]
+        if len(bad):
+            s = self.states[bad[0]]
+            raise RuntimeError("Numerov integration failed for %d state(s); first: index %d (l=%d, j=%.1f, "
+                               "E=%.6g a.u.), status %d" % (len(bad), bad[0], s["l"], s["j"], s["stateEnergy"],
+                                                            st[bad[0]]))
 
     def wavefunction(self, i):
         """(r, psi) of state i as numpy arrays (device -> host copy)."""
@@ -105,7 +126,7 @@ class RadialBatch:
     def integrals(self, pairs):
         return self.integrals_device(pairs).cpu().numpy()
 
-    def integrals_sharded(self, pairs, group=None):
+    def integrals_sharded(self, pairs, group="world"):
         """integrals_device with the pairs sharded over the ranks of `group` and the results
         all-gathered (every rank holds all wavefunctions: Numerov is ~10 % of a table)."""
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)

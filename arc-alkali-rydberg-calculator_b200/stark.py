@@ -152,10 +152,12 @@ class StarkMap:
         return 0
 
     def diagonalise(self, eFieldList, drivingFromState=[0, 0, 0, 0, 0], progressOutput=False,
-                    debugOutput=False, upTo=4, totalContributionMax=0.95, batch=None):
+                    debugOutput=False, upTo=4, totalContributionMax=0.95, batch=None, group=None):
         """calculations_atom_single.py:846-1025.  Results: `y` (list of ascending
         eigenvalue arrays, GHz), `highlight`, `composition` -- same indexing as the
-        reference; eigenvectors never leave the GPU."""
+        reference; eigenvectors never leave the GPU.  `group` (extension): None = all fields
+        on this GPU; sweep.WORLD or a torch.distributed group = fields sharded over its ranks
+        (collective call, every rank gets the full result)."""
         dimension = len(self.basisStates)
         self.maxCoupling = 0.0
         self.drivingFromState = drivingFromState
@@ -186,7 +188,7 @@ class StarkMap:
         res = _sweep.stark_sweep(np.diag(self.mat1).copy(), self.mat2, fields,
                                  self.indexOfCoupledState, drive_w=drive_w, topk=topk,
                                  contrib_max=cmax, device=getattr(self.atom, "device", None),
-                                 batch=batch)
+                                 batch=batch, group=group)
         self.last_sweep = res
         self.gpu_kernel_launches += res.kernel_launches
         self.y = [res.y[f] for f in range(len(fields))]

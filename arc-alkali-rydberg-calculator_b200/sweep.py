@@ -5,6 +5,11 @@ share H0 and V (or matDiagonal and matR), so they shard with NO data-path
 collective: rank g of G takes the contiguous slice points[g*P/G:(g+1)*P/G]
 (SURVEY.md 8e), solves it on its own GPU, and the per-rank results are
 all-gathered once at the end (NCCL on GPUs; gloo in the CPU tests).
+
+Sharding is OPT-IN: every entry point takes `group=None` (= this process solves all
+points, no collective is ever entered).  Pass `group=WORLD` (the default process group)
+or a `torch.distributed` ProcessGroup to shard; the call is then collective and every
+rank of the group has to make it.
 """
 import numpy as np
 
@@ -18,18 +23,26 @@ def shard_bounds(npoints, rank, world):
     return lo, hi
 
 
+WORLD = "world"      # group=WORLD: shard over the default torch.distributed process group
+
+
+def _pg(group):
+    return None if (isinstance(group, str) and group == WORLD) else group
+
+
 def dist_info(group=None):
-    """(rank, world) of the default process group, (0, 1) when not initialised."""
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(group), dist.get_world_size(group)
-    except Exception:
-        pass
-    return 0, 1
+    """(rank, world) of `group`; (0, 1) for group=None (no sharding requested).  A group was
+    asked for but torch.distributed is not initialised -> error (a silent single-rank run of
+    a call the user meant to be collective would solve everything on every rank)."""
+    if group is None:
+        return 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("group=%r requested but torch.distributed is not initialised" % (group,))
+    return dist.get_rank(_pg(group)), dist.get_world_size(_pg(group))
 
 
-def gather_rows(local, npoints, group=None):
+def gather_rows(local, npoints, group=WORLD):
     """All-gather per-rank row blocks (torch tensors, first dim = local points) into the
     full [npoints, ...] tensor on every rank.  Ragged shards are padded to the largest."""
     import torch
@@ -42,7 +55,7 @@ def gather_rows(local, npoints, group=None):
     pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:local.shape[0]] = local
     outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad, group=group)
+    dist.all_gather(outs, pad, group=_pg(group))
     return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
 
 
@@ -87,15 +100,16 @@ class SweepResult:
 
 
 def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
-                device=None, batch=None, distributed=True, to_host=True):
-    """Solve H = diag(h0) + F*V for every F (calculations_atom_single.py:976-1021)."""
+                device=None, batch=None, group=None, to_host=True):
+    """Solve H = diag(h0) + F*V for every F (calculations_atom_single.py:976-1021).
+    group=None: all fields on this GPU; group=WORLD / a ProcessGroup: collective, sharded."""
     import torch
     lib = _lib.load()
     device = _lib.require_device(device)
     dev = torch.device("cuda", device)
     fields = np.ascontiguousarray(fields, dtype=np.float64)
     nF_all = len(fields)
-    rank, world = dist_info() if distributed else (0, 1)
+    rank, world = dist_info(group)
     lo, hi = shard_bounds(nF_all, rank, world)
     nF = hi - lo
     N = int(len(h0diag))
@@ -111,6 +125,7 @@ def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
     hl = torch.empty((nF, N), dtype=torch.float64, device=dev)
     comp_c = torch.zeros((nF, N, max(topk, 1)), dtype=torch.float64, device=dev)
     comp_i = torch.full((nF, N, max(topk, 1)), -1, dtype=torch.int32, device=dev)
+    nl = _lib.LaunchCount()
     if nF > 0:
         b = _pick_batch(N, nF, N, device, batch)
         wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, N))
@@ -119,14 +134,14 @@ def stark_sweep(h0diag, V, fields, idx0, drive_w=None, topk=3, contrib_max=0.95,
                                      _lib.ptr(d_V), nF, _lib.ptr(d_F), int(idx0),
                                      _lib.ptr(d_w), int(topk), float(contrib_max),
                                      _lib.ptr(y), _lib.ptr(hl), _lib.ptr(comp_c),
-                                     _lib.ptr(comp_i), _lib.ptr(work), wbytes, b)
+                                     _lib.ptr(comp_i), _lib.ptr(work), wbytes, b, nl.addr)
         _lib.check(rc, "arcb200_stark_sweep")
-        res.kernel_launches = rc
+        res.kernel_launches = nl.value
     else:
         res.kernel_launches = 0
     if world > 1:
-        y, hl = gather_rows(y, nF_all), gather_rows(hl, nF_all)
-        comp_c, comp_i = gather_rows(comp_c, nF_all), gather_rows(comp_i, nF_all)
+        y, hl = gather_rows(y, nF_all, group), gather_rows(hl, nF_all, group)
+        comp_c, comp_i = gather_rows(comp_c, nF_all, group), gather_rows(comp_i, nF_all, group)
     if to_host:
         res.y, res.hl = y.cpu().numpy(), hl.cpu().numpy()
         res.comp_c, res.comp_i = comp_c.cpu().numpy(), comp_i.cpu().numpy()
@@ -158,11 +173,12 @@ def floquet_sweep(h0diag, B, fields, idx0, dim0, device=None, batch=None, d_B=No
     b = _pick_batch(N, nF, N, device, batch)
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, N))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    nl = _lib.LaunchCount()
     rc = lib.arcb200_floquet_sweep(device, _lib.stream_ptr(device), N, int(dim0), _lib.ptr(d_h0),
                                    _lib.ptr(d_B), nF, _lib.ptr(d_F), int(idx0), _lib.ptr(y),
-                                   _lib.ptr(hl), _lib.ptr(tp), _lib.ptr(work), wbytes, b)
+                                   _lib.ptr(hl), _lib.ptr(tp), _lib.ptr(work), wbytes, b, nl.addr)
     _lib.check(rc, "arcb200_floquet_sweep")
-    return y.cpu().numpy(), hl.cpu().numpy(), tp.cpu().numpy(), rc
+    return y.cpu().numpy(), hl.cpu().numpy(), tp.cpu().numpy(), nl.value
 
 
 class PairOperators:
@@ -195,16 +211,17 @@ class PairOperators:
 
 
 def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max=0.95, batch=None,
-               distributed=True, to_host=True, want_overlap=False):
+               group=None, to_host=True, want_overlap=False):
     """k eigenpairs nearest sigma of H(R) for every R (already sorted by the caller,
-    calculations_atom_pairstate.py:3307, 3425-3520)."""
+    calculations_atom_pairstate.py:3307, 3425-3520).
+    group=None: all points on this GPU; group=WORLD / a ProcessGroup: collective, sharded."""
     import torch
     lib = _lib.load()
     device = ops.device
     dev = torch.device("cuda", device)
     rangeR = np.ascontiguousarray(rangeR, dtype=np.float64)
     nR_all = len(rangeR)
-    rank, world = dist_info() if distributed else (0, 1)
+    rank, world = dist_info(group)
     lo, hi = shard_bounds(nR_all, rank, world)
     # overlaps chain consecutive points: a shard also solves the point before its first one
     # (one redundant solve per rank instead of a peer-to-peer exchange of N x k eigenvectors)
@@ -224,6 +241,7 @@ def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max
     comp_c = torch.zeros((nR, k, max(topk, 1)), dtype=torch.float64, device=dev)
     comp_i = torch.full((nR, k, max(topk, 1)), -1, dtype=torch.int32, device=dev)
     ov = torch.empty((nR, k, k), dtype=torch.float64, device=dev) if want_overlap else None
+    nl = _lib.LaunchCount()
     if nR > 0:
         b = _pick_batch(N, nR, k, device, batch)
         wbytes = int(lib.arcb200_sweep_workspace_bytes(N, b, k)) + (N * k * 8 + 256 if want_overlap else 0)
@@ -233,18 +251,18 @@ def pair_sweep(ops, rangeR, k, sigma_ghz, opi, drive_w=None, topk=4, contrib_max
                                     int(k), float(sigma_ghz), int(opi), _lib.ptr(d_w),
                                     int(topk), float(contrib_max), _lib.ptr(y), _lib.ptr(hl),
                                     _lib.ptr(comp_c),
-                                    _lib.ptr(comp_i), _lib.ptr(ov), _lib.ptr(work), wbytes, b)
+                                    _lib.ptr(comp_i), _lib.ptr(ov), _lib.ptr(work), wbytes, b, nl.addr)
         _lib.check(rc, "arcb200_pair_sweep")
-        res.kernel_launches = rc
+        res.kernel_launches = nl.value
     else:
         res.kernel_launches = 0
     if lead:      # drop the redundant leading point (its overlap row belongs to the previous rank)
         y, hl, comp_c, comp_i, ov = y[1:], hl[1:], comp_c[1:], comp_i[1:], ov[1:]
     if world > 1:
-        y, hl = gather_rows(y, nR_all), gather_rows(hl, nR_all)
-        comp_c, comp_i = gather_rows(comp_c, nR_all), gather_rows(comp_i, nR_all)
+        y, hl = gather_rows(y, nR_all, group), gather_rows(hl, nR_all, group)
+        comp_c, comp_i = gather_rows(comp_c, nR_all, group), gather_rows(comp_i, nR_all, group)
         if ov is not None:
-            ov = gather_rows(ov, nR_all)
+            ov = gather_rows(ov, nR_all, group)
     if ov is not None:
         res.overlap = ov.cpu().numpy() if to_host else ov
     if to_host:
@@ -274,7 +292,7 @@ def syevd_batched(A, device=None):
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     rc = lib.arcb200_syevd_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
-                                   _lib.ptr(d_w), _lib.ptr(d_Z), _lib.ptr(work), wbytes)
+                                   _lib.ptr(d_w), _lib.ptr(d_Z), _lib.ptr(work), wbytes, 0)
     _lib.check(rc, "arcb200_syevd_batched")
     return d_w.cpu().numpy(), np.ascontiguousarray(d_Z.cpu().numpy().transpose(0, 2, 1))
 
@@ -295,7 +313,7 @@ def sytrd_batched(A, cluster=0, device=None):
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     rc = lib.arcb200_sytrd_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
                                    _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
-                                   _lib.ptr(work), wbytes, int(cluster))
+                                   _lib.ptr(work), wbytes, int(cluster), 0)
     _lib.check(rc, "arcb200_sytrd_batched")
     return [o.cpu().numpy() for o in outs]
 
@@ -316,7 +334,7 @@ def sy2sb_batched(A, device=None):
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, batch, N))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     rc = lib.arcb200_sy2sb_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_A),
-                                   _lib.ptr(band), _lib.ptr(work), wbytes)
+                                   _lib.ptr(band), _lib.ptr(work), wbytes, 0)
     _lib.check(rc, "arcb200_sy2sb_batched")
     return band.cpu().numpy()
 
@@ -338,6 +356,6 @@ def stedc_batched(d, e, device=None):
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     rc = lib.arcb200_stedc_batched(device, _lib.stream_ptr(device), N, batch, _lib.ptr(d_d),
                                    _lib.ptr(d_e), _lib.ptr(d_w), _lib.ptr(d_Q), _lib.ptr(work),
-                                   wbytes)
+                                   wbytes, 0)
     _lib.check(rc, "arcb200_stedc_batched")
     return d_w.cpu().numpy(), np.ascontiguousarray(d_Q.cpu().numpy().transpose(0, 2, 1))

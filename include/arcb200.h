@@ -10,7 +10,9 @@
  *   - `device` is the CUDA ordinal, `stream` a cudaStream_t passed as void*
  *     (NULL = legacy default stream);
  *   - return value 0 = success, negative = error; arcb200_last_error() returns a
- *     thread-local message.  Nothing calls exit()/abort() (the reference's C
+ *     thread-local message.  Entry points that launch a variable number of kernels report
+ *     the count through a trailing `int32_t *h_launches` (host pointer, may be NULL);
+ *     per-item failures come back in device status arrays (d_status), never as aborts.  Nothing calls exit()/abort() (the reference's C
  *     extension returns NULL without setting an exception, arc_c_extensions.c:145,200);
  *   - re-entrant per (device, stream); no file-scope state (the reference keeps all
  *     integrator state in globals, arc_c_extensions.c:11-24,57-67).
@@ -23,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ARCB200_ABI_VERSION 1
+#define ARCB200_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------ */
 /* library                                                                   */
@@ -38,6 +40,8 @@ int arcb200_device_info(int device, int64_t *props);
  * only: the denominator of the roofline of the DMMA-bound eigensolver kernels (the driver's
  * MEASURED_PEAKS.json has no FP64 figure).  d_scratch: one device double. */
 int arcb200_dmma_peak(int device, void *stream, double *d_scratch, double *h_tflops);
+/* Same for the plain FP64 FMA pipe (DFMA), 16 independent chains per thread. */
+int arcb200_dfma_peak(int device, void *stream, double *d_scratch, double *h_tflops);
 
 /* ------------------------------------------------------------------------ */
 /* subsystem (1): Numerov radial wavefunctions + radial integrals            */
@@ -70,11 +74,15 @@ int64_t arcb200_numerov_lengths(int32_t nstates, arcb200_state_t *h_states,
  *                      divergence point
  *   d_r    = r grid   (the C extension's row 1)
  *   d_norm[i] = trapezoid(psi_raw^2, r);  d_dp[i] = divergencePoint
+ *   d_status[i] (may be NULL) = 0 ok | 1 the outward walk left the integrated range (the
+ *                reference's "Numerov error", arc_c_extensions.c:196-201: returns NULL)
+ *                | 2 norm not finite or not positive (no usable wavefunction)
  * d_order = processing order (state indices, longest first) or NULL. */
 int arcb200_numerov_batch(int device, void *stream, int32_t nstates,
                           const arcb200_state_t *d_states, const int64_t *d_offsets,
                           const int32_t *d_order, double *d_psi, double *d_r,
-                          double *d_norm, int32_t *d_dp, int32_t normalise);
+                          double *d_norm, int32_t *d_dp, int32_t normalise,
+                          int32_t *d_status);
 
 /* Batched radial overlap integrals, one warp per pair:
  *   out[p] = trapezoid(psi_a*psi_b*r_a^power, x=r_a)[0:min(La,Lb)]
@@ -132,7 +140,9 @@ int64_t arcb200_sweep_workspace_bytes(int32_t N, int32_t batch, int32_t nvec);
  *            = sum_j drive_w[j] |v[j,i]|^2   otherwise
  *   comp_c/comp_i[f][i][0..topk) = coefficient/index of the largest |v[:,i]|
  *            entries, descending, stopping once sum c^2 >= contrib_max
- *            (unused slots: index -1)
+ *            (unused slots: index -1); any topk <= N: up to 8 entries come from the fused
+ *            epilogue, more (upTo = -1 -> topk = N, contrib_max = 2) from a full sort of
+ *            the eigenvector by |c| (calculations_atom_single.py:1399-1407)
  * Replaces the loop body of StarkMap.diagonalise
  * (calculations_atom_single.py:976-1021, _stateComposition2 1395-1416,
  *  numpy.linalg.eigh at 986). */
@@ -140,7 +150,7 @@ int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0d
                         const double *d_V, int32_t nF, const double *d_F, int32_t idx0,
                         const double *d_drive_w, int32_t topk, double contrib_max,
                         double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
-                        void *d_work, int64_t work_bytes, int32_t batch);
+                        void *d_work, int64_t work_bytes, int32_t batch, int32_t *h_launches);
 
 /* Floquet (Shirley) sweep: for every field amplitude F[f]:  H = diag(h0) + F[f]*B, N = dim0 *
  * (2 fn + 1) (the caller folds the drive frequency into h0 = tile(bareEnergies) + k*freq),
@@ -152,7 +162,8 @@ int arcb200_stark_sweep(int device, void *stream, int32_t N, const double *d_h0d
 int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_t dim0,
                           const double *d_h0diag, const double *d_B, int32_t nF,
                           const double *d_F, int32_t idx0, double *d_y, double *d_hl,
-                          double *d_tprob, void *d_work, int64_t work_bytes, int32_t batch);
+                          double *d_tprob, void *d_work, int64_t work_bytes, int32_t batch,
+                          int32_t *h_launches);
 
 /* Pair-energy scan of StarkMapResonances.findResonances
  * (calculations_atom_pairstate.py:4753-4789): keeps the pairs (j, jj) of single-atom Stark
@@ -181,7 +192,8 @@ int arcb200_pair_sweep(int device, void *stream, int32_t N, const double *d_h0di
                        const double *d_R, int32_t k, double sigma, int32_t opi,
                        const double *d_drive_w, int32_t topk, double contrib_max,
                        double *d_y, double *d_hl, double *d_comp_c, int32_t *d_comp_i,
-                       double *d_overlap, void *d_work, int64_t work_bytes, int32_t batch);
+                       double *d_overlap, void *d_work, int64_t work_bytes, int32_t batch,
+                       int32_t *h_launches);
 
 /* Sparse (COO) -> dense scatter used to stage matR[o] on the device
  * (the reference keeps matR as scipy CSR, calculations_atom_pairstate.py:3230-3239). */
@@ -196,25 +208,26 @@ int arcb200_scatter_coo(int device, void *stream, int32_t N, int64_t nnz,
  * d_Z[b][i][0..N) (row i = vector i). */
 int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_t batch,
                           double *d_A, double *d_w, double *d_Z, void *d_work,
-                          int64_t work_bytes);
+                          int64_t work_bytes, int32_t *h_launches);
 
 /* Stage-level entry points of the eigensolver (LAPACK dsytrd / dstedc equivalents),
  * exposed for the stage parity tests.  d_A: batch x N x N symmetric; outputs d, e, tau
  * (batch x N each; e[N-1], tau[N-1] unused).  cluster = CTAs per matrix (0 = auto). */
 int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
                           const double *d_A, double *d_d, double *d_e, double *d_tau,
-                          void *d_work, int64_t work_bytes, int32_t cluster);
+                          void *d_work, int64_t work_bytes, int32_t cluster, int32_t *h_launches);
 /* (d, e) -> eigenvalues d_w (ascending) and eigenvectors of the tridiagonal matrix,
  * d_Q[b][i][0..N) = eigenvector i. */
 int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
                           const double *d_d, const double *d_e, double *d_w, double *d_Q,
-                          void *d_work, int64_t work_bytes);
+                          void *d_work, int64_t work_bytes, int32_t *h_launches);
 /* Stage 1 of the two-stage path alone (dense -> band of width 32, mid-sized N only; when the
  * two-stage path is active arcb200_sytrd_batched with cluster = 0 runs both of its stages and
  * returns the tridiagonal d, e; tau is then per band-reduction reflector).
  * d_band[b][j][d] = B[j+d][j], d = 0..32 (batch x N x 33). */
 int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_t batch,
-                          const double *d_A, double *d_band, void *d_work, int64_t work_bytes);
+                          const double *d_A, double *d_band, void *d_work, int64_t work_bytes,
+                          int32_t *h_launches);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libarcb200.so does not export %s" % n
     # the ctypes table binds exactly the declared entry points
     assert sorted(_lib.exported_symbols()) == names
-    assert _lib.load().arcb200_abi_version() == 1
+    assert _lib.load().arcb200_abi_version() == 2
 
 
 def test_state_struct_layout_and_lengths():

@@ -23,7 +23,8 @@ def _worker(rank, world, port, npoints, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        assert sweep.dist_info() == (rank, world)
+        assert sweep.dist_info() == (0, 1)              # sharding is opt-in
+        assert sweep.dist_info(sweep.WORLD) == (rank, world)
         lo, hi = sweep.shard_bounds(npoints, rank, world)
         # every rank "solves" its own shard: row p holds f(p)
         local = torch.stack([torch.arange(4, dtype=torch.float64) + 10.0 * p for p in range(lo, hi)]) \

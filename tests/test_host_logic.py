@@ -89,6 +89,31 @@ def test_stark_define_basis_host_logic(gold_dir):
     assert np.array_equal(calc.mat2, calc.mat2.T)
 
 
+@pytest.mark.parametrize("name,cls", [("stark_rb_lown_golden.npz", "Rubidium"),
+                                      ("stark_k_lown_golden.npz", "Potassium")])
+def test_stark_basis_below_ground_state_matches_reference(gold_dir, name, cls):
+    """nMin < groundStateN.  The reference tests `[tn, tl, tj] in atom.extraLevels` with a list
+    against a list of TUPLES (calculations_atom_single.py:749-751, alkali_atom_data.py:286-295),
+    which is never true: every state below groundStateN is dropped, extra levels included.
+    Golden from the live reference pins that behaviour."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, name))
+    atom = patch_atom_with_oracle(getattr(arc_b200, cls)())
+    calc = arc_b200.StarkMap(atom)
+    a = g["args"]
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]))
+    got = np.array(calc.basisStates)
+    assert got.shape == g["basisStates"].shape and np.allclose(got, g["basisStates"])
+    assert atom.extraLevels and not (got[:, 0] < atom.groundStateN).any()
+    assert calc.indexOfCoupledState == int(g["indexOfCoupledState"])
+    assert np.abs(np.diag(calc.mat1) - g["mat1_diag"]).max() <= 1e-12 * np.abs(g["mat1_diag"]).max()
+    N = len(g["mat1_diag"])
+    m2 = np.zeros((N, N))
+    m2[g["mat2_rows"], g["mat2_cols"]] = g["mat2_vals"]
+    assert np.array_equal(calc.mat2 != 0, m2 != 0)
+    assert np.abs(calc.mat2 - m2).max() <= 1e-8 * np.abs(m2).max()
+
+
 def test_composition_view_and_pickle():
     from arc_b200.stark import CompositionView
     c = np.array([[[0.9, -0.3, 0.0], [1.0, 0.0, 0.0]]])

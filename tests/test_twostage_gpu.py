@@ -125,7 +125,7 @@ def test_stark_sweep_in_two_stage_window():
     V = V + V.T
     F = np.linspace(0.0, 2.0, nF)
     idx0 = N // 2
-    r = sweep.stark_sweep(h0, V, F, idx0, topk=3, distributed=False)
+    r = sweep.stark_sweep(h0, V, F, idx0, topk=3)
     for f in range(nF):
         w0, v0 = np.linalg.eigh(np.diag(h0) + F[f] * V)
         scale = np.abs(w0).max()
@@ -151,7 +151,7 @@ def test_pair_sweep_window_in_two_stage_window():
     ops = sweep.PairOperators(h0, [(r, c, M[r, c])], N)
     R = np.array([6.0, 2.5, 1.2])
     for k, sigma in ((37, 0.0), (250, 0.9)):
-        res = sweep.pair_sweep(ops, R, k, sigma, opi=17, distributed=False)
+        res = sweep.pair_sweep(ops, R, k, sigma, opi=17)
         for i, rv in enumerate(R):
             H = np.diag(h0) + M / (rv * 1e-6) ** 3
             w, v = np.linalg.eigh(H)

@@ -12,7 +12,7 @@ calc.defineBasis(0., 0., 5, 5, 25e9)
 ops = calc.device_operators()
 R = np.sort(np.resize(np.linspace(1, 10, 1000), npts))[::-1].copy()
 def step():
-    return sweep.pair_sweep(ops, R, 250, 0.0, calc.originalPairStateIndex, topk=4, distributed=False, to_host=False)
+    return sweep.pair_sweep(ops, R, 250, 0.0, calc.originalPairStateIndex, topk=4, to_host=False)
 r0 = step(); torch.cuda.synchronize()
 ref = os.environ.get("AB_REF")
 y = r0.y.cpu().numpy()

@@ -10,7 +10,7 @@ lib = _lib.load(); dev = torch.device("cuda", 0)
 A = torch.randn((nb, N, N), dtype=torch.float64, device=dev); A = A + A.transpose(1, 2).contiguous()
 w = torch.zeros((nb, N), dtype=torch.float64, device=dev); Z = torch.zeros((nb, N, N), dtype=torch.float64, device=dev)
 wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N)); work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-def f(): _lib.check(lib.arcb200_syevd_batched(0, _lib.stream_ptr(0), N, nb, _lib.ptr(A), _lib.ptr(w), _lib.ptr(Z), _lib.ptr(work), wbytes), "syevd")
+def f(): _lib.check(lib.arcb200_syevd_batched(0, _lib.stream_ptr(0), N, nb, _lib.ptr(A), _lib.ptr(w), _lib.ptr(Z), _lib.ptr(work), wbytes, 0), "syevd")
 f(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); f(); f(); e1.record(); torch.cuda.synchronize()

@@ -10,7 +10,7 @@ d_A = torch.as_tensor(A).to(dev)
 outs = [torch.zeros((nb, N), dtype=torch.float64, device=dev) for _ in range(3)]
 wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N)); work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
 def sy():
-    _lib.check(lib.arcb200_sytrd_batched(0, _lib.stream_ptr(0), N, nb, _lib.ptr(d_A), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(work), wbytes, cl), "sytrd")
+    _lib.check(lib.arcb200_sytrd_batched(0, _lib.stream_ptr(0), N, nb, _lib.ptr(d_A), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(work), wbytes, cl, 0), "sytrd")
 sy(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); sy(); e1.record(); torch.cuda.synchronize()

@@ -42,8 +42,8 @@ if tb:
     outs = [torch.zeros((tb, N), dtype=torch.float64, device=dev) for _ in range(3)]
     band = torch.zeros((tb, N, 33), dtype=torch.float64, device=dev)
     wbytes = int(lib.arcb200_sweep_workspace_bytes(N, tb, N)); work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    def f1(): _lib.check(lib.arcb200_sy2sb_batched(0, _lib.stream_ptr(0), N, tb, _lib.ptr(d_A), _lib.ptr(band), _lib.ptr(work), wbytes), "sy2sb")
-    def f2(): _lib.check(lib.arcb200_sytrd_batched(0, _lib.stream_ptr(0), N, tb, _lib.ptr(d_A), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(work), wbytes, 0), "sytrd")
+    def f1(): _lib.check(lib.arcb200_sy2sb_batched(0, _lib.stream_ptr(0), N, tb, _lib.ptr(d_A), _lib.ptr(band), _lib.ptr(work), wbytes, 0), "sy2sb")
+    def f2(): _lib.check(lib.arcb200_sytrd_batched(0, _lib.stream_ptr(0), N, tb, _lib.ptr(d_A), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(work), wbytes, 0, 0), "sytrd")
     for name, f in (("sy2sb", f1), ("sy2sb+sb2st", f2)):
         f(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -337,6 +337,35 @@ def gen_divalent(arc):
                 "stark_sr88_singlet_golden.npz", kwargs={"s": 0})
 
 
+def gen_lown(arc):
+    """Stark basis that reaches below groundStateN: the reference keeps the states listed in
+    atom.extraLevels (Rb 4D, 4F; K 3D) and drops the other n < groundStateN states."""
+    _stark_case(arc, arc.Rubidium(), (6, 0, 0.5, 0.5, 4, 7, 3), np.linspace(0, 1e5, 3),
+                "stark_rb_lown_golden.npz")
+    _stark_case(arc, arc.Potassium(), (5, 0, 0.5, 0.5, 3, 6, 2), np.linspace(0, 1e5, 3),
+                "stark_k_lown_golden.npz")
+
+
+def gen_c4(arc, which):
+    """C4 (BASELINE.json configs[3]) at its stated size: Sr88 n=50-70, lmax=30, singlet N=651 /
+    triplet N=1932; 8 of the 2000 fields kept."""
+    a = arc.Strontium88()
+    F = np.linspace(0, 200, 2000)[[0, 1, 250, 700, 1000, 1400, 1750, 1999]]
+    if which == "singlet":
+        _stark_case(arc, a, (60, 0, 0, 0, 50, 70, 30), F, "stark_c4_singlet_golden.npz", kwargs={"s": 0})
+    else:
+        _stark_case(arc, a, (60, 0, 1, 0, 50, 70, 30), F, "stark_c4_triplet_golden.npz", kwargs={"s": 1})
+
+
+def gen_c5(arc):
+    """C5 (BASELINE.json configs[4]) at its stated size: Rb 80D5/2+80D5/2, theta=pi/4, Bz=1e-4 T,
+    nRange=3, lrange=4, 10 GHz -> N=10384; 2 of the 4096 R points."""
+    a = arc.Rubidium()
+    R = np.linspace(2, 20, 4096)[[600, 3500]]
+    _pair_case(arc, a, (80, 2, 2.5, 80, 2, 2.5, 2.5, 2.5), (np.pi / 4, 0, 3, 4, 10e9, 1e-4),
+               list(R), 250, "pair_c5_golden.npz")
+
+
 def gen_driving(arc):
     """drivingFromState variants: highlight = laser-coupling weighted admixture
     (calculations_atom_single.py:887-962,1003-1021; calculations_atom_pairstate.py:3332-3413,3507-3520)."""
@@ -505,6 +534,14 @@ if __name__ == "__main__":
         gen_pair(arc, big=True)
     if "divalent" in what:
         gen_divalent(arc)
+    if "lown" in what:
+        gen_lown(arc)
+    if "c4singlet" in what:
+        gen_c4(arc, "singlet")
+    if "c4triplet" in what:
+        gen_c4(arc, "triplet")
+    if "c5" in what:
+        gen_c5(arc)
     if "driving" in what:
         gen_driving(arc)
     if "sorted" in what:

@@ -9,6 +9,6 @@ calc.defineBasis(28, 0, 0.5, 0.5, 23, 32, 20)
 F = np.linspace(0, 600, 600)
 h0 = np.diag(calc.mat1).copy()
 for it in range(2):
-    r = sweep.stark_sweep(h0, calc.mat2, F, calc.indexOfCoupledState, distributed=False, to_host=False)
+    r = sweep.stark_sweep(h0, calc.mat2, F, calc.indexOfCoupledState, to_host=False)
 torch.cuda.synchronize()
 print("launches per sweep", r.kernel_launches)

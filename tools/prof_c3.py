@@ -9,6 +9,6 @@ calc = bench.build_c3()
 ops = calc.device_operators()
 R = np.linspace(10.0, 1.0, npts)
 for it in range(2):
-    r = sweep.pair_sweep(ops, R, 250, 0.0, calc.originalPairStateIndex, topk=4, distributed=False, to_host=False)
+    r = sweep.pair_sweep(ops, R, 250, 0.0, calc.originalPairStateIndex, topk=4, to_host=False)
 torch.cuda.synchronize()
 print("launches per sweep", r.kernel_launches)
