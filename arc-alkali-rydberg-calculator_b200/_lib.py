@@ -34,6 +34,8 @@ _SIGNATURES = {
     "arcb200_numerov_lengths": (c_i64, [c_i32, c_vp, c_vp]),
     "arcb200_numerov_batch": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                                       c_vp, c_vp, c_i32, c_vp]),
+    "arcb200_numerov_coeff_batch": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                            c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_radial_integrals": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_vp]),
     "arcb200_radial_gram": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -194,11 +194,40 @@ class AlkaliAtom:
                                   self.alphaC, self.alpha, self.Z, p[0], p[1], p[2],
                                   p[3], p[4], mu)
 
+    # model potential of the valence electron (alkali_atom_functions.py:431-501); numpy
+    # expressions, so they accept scalars and grids alike
+    def effectiveCharge(self, l, r):
+        return (1.0 + (self.Z - 1) * np.exp(-self.a1[l] * r)
+                - r * (self.a3[l] + self.a4[l] * r) * np.exp(-self.a2[l] * r))
+
+    def corePotential(self, l, r):
+        return -self.effectiveCharge(l, r) / r - self.alphaC / (2 * r ** 4) * (
+            1 - np.exp(-((r / self.rc[l]) ** 6)))
+
+    def potential(self, l, s, j, r):
+        so = self.alpha ** 2 / (2.0 * r ** 3) * (j * (j + 1.0) - l * (l + 1.0) - s * (s + 1)) / 2.0
+        if l < 4:
+            return self.corePotential(l, r) + so
+        return -1.0 / r + so
+
     def radialWavefunction(self, l, s, j, stateEnergy, innerLimit, outerLimit, step):
         """(r, R(r)*r normalised) -- alkali_atom_functions.py:503-625, computed by the
-        batched CUDA Numerov kernel (batch of one)."""
+        batched CUDA Numerov kernel (batch of one).  With cpp_numerov=False the reference's
+        pure-Python route (aaf:606-623: NumerovBack on a callable k(x)) is taken instead: k(x) is
+        evaluated on the host grid, the recurrence runs in numerov_coeff_kernel."""
         innerLimit = max(4.0 * step, innerLimit)
         mu = (self.mass - C_m_e) / self.mass
+        if not self.cpp_numerov:
+            from .numerov import NumerovBack
+
+            def potential(x):
+                r = x * x
+                return -3.0 / (4.0 * r) + 4.0 * r * (
+                    2.0 * mu * (stateEnergy - self.potential(l, s, j, r)) - l * (l + 1) / (r ** 2))
+            r, psi_r = NumerovBack(innerLimit, outerLimit, potential, step, 0.01, 0.01)
+            self.gpu_kernel_launches += 1
+            suma = np.trapezoid(psi_r ** 2, x=r)
+            return r, psi_r / np.sqrt(suma)
         if l < 4:
             p = (self.a1[l], self.a2[l], self.a3[l], self.a4[l], self.rc[l])
         else:
@@ -277,7 +306,7 @@ class AlkaliAtom:
                 blocks.append((ra, cb, gk[4]))
                 for t in ts:
                     where[t] = (g, ia[int(pair_rows[t, 0])] * len(cb) + ib[int(pair_rows[t, 1])])
-            out, offs, _nref = rb.gram_refined_device(blocks, thresh=1e-4)
+            out, offs, _nref = rb.gram_refined_device(blocks, thresh=_radial.GRAM_REFINE_THRESH)
             out = out.cpu().numpy()
             vals = np.array([out[offs[g] + e] for g, e in where])
         self.gpu_kernel_launches += rb.kernel_launches

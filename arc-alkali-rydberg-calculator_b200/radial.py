@@ -27,6 +27,13 @@ def make_state(innerLimit, outerLimit, step, init1, init2, l, s, j, stateEnergy,
     return rec
 
 
+# Gram path: elements with |value| < GRAM_REFINE_THRESH * sqrt(<r^p>_a <r^p>_b) are recomputed by
+# the exact per-pair kernel.  The tensor-core table differs from the per-pair formula by up to
+# 3e-12 of that Cauchy-Schwarz scale (common r grid, summation order), i.e. 3e-9 relative at the
+# threshold: inside the 1e-8 matrix-element tolerance for every element of the table.
+GRAM_REFINE_THRESH = 1e-3
+
+
 def sharded_table(compute, pairs, group="world"):
     """One matrix-element table for all ranks of the process group: rank g evaluates the
     contiguous shard pairs[g*P/G:(g+1)*P/G] with `compute(shard) -> tensor[len(shard)]` and
@@ -180,7 +187,7 @@ class RadialBatch:
             self._moments = self.integrals_device(pr).reshape(2, self.n).t().contiguous()
         return self._moments
 
-    def gram_refined_device(self, blocks, thresh=1e-5):
+    def gram_refined_device(self, blocks, thresh=GRAM_REFINE_THRESH):
         """Gram tables with per-element accuracy control.  The tensor-core sums carry an
         absolute rounding error of ~2e-14 * int|psi_a psi_b| r^p; for strongly cancelling
         elements (|value| < thresh * sqrt(<r^p>_a <r^p>_b), physically ~zero couplings) that

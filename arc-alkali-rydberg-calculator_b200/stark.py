@@ -196,6 +196,35 @@ class StarkMap:
         self.composition = CompositionView(res.comp_c, res.comp_i)
         return
 
+    def getState(self, state, electricField, minN, maxN, maxL, accountForAmplitude=0.95,
+                 debugOutput=False):
+        """calculations_atom_single.py:1577-1668: basis states and coefficients of the eigenstate
+        (at the given field) that carries most of `state`, sorted by declining contribution until
+        `accountForAmplitude` of the norm is covered, and its energy in eV.  One GPU eigensolve with
+        the full sorted composition (upTo = -1) instead of the host `eigh` + argsort; the overall
+        sign of the coefficient vector is the eigensolver's (arbitrary in the reference as well)."""
+        self.defineBasis(state[0], state[1], state[2], state[3], minN, maxN, maxL)
+        N = len(self.basisStates)
+        res = _sweep.stark_sweep(np.diag(self.mat1).copy(), self.mat2, np.array([float(electricField)]),
+                                 self.indexOfCoupledState, topk=N, contrib_max=2.0,
+                                 device=getattr(self.atom, "device", None))
+        self.gpu_kernel_launches += res.kernel_launches
+        # strongest contribution of the requested state: first maximum, like the strict `>` scan
+        eigenvectorIndex = int(np.argmax(res.hl[0]))
+        energy = res.y[0][eigenvectorIndex] * 1e9 * C_h / C_e
+        if debugOutput:
+            print("Max overlap = %.3f" % res.hl[0][eigenvectorIndex])
+            print("Eigen energy (state index %d) = %.2f eV" % (eigenvectorIndex, energy))
+        c, ix = res.comp_c[0][eigenvectorIndex], res.comp_i[0][eigenvectorIndex]
+        i = 0
+        coef, contributingStates = [], []
+        while accountForAmplitude > 0 and i < N:
+            coef.append(c[i])
+            accountForAmplitude -= abs(coef[-1]) ** 2
+            contributingStates.append(self.basisStates[int(ix[i])])
+            i += 1
+        return contributingStates, coef, energy
+
     def _addState(self, n1, l1, j1, mj1):
         """calculations_atom_single.py:1418-1430."""
         from .pairstate import printStateStringLatex

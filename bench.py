@@ -534,7 +534,7 @@ def bench_c2(args):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rb.gram_refined_device(blocks, thresh=1e-4)
+            rb.gram_refined_device(blocks, thresh=radial.GRAM_REFINE_THRESH)
             e1.record()
             torch.cuda.synchronize()
             tg.append(e0.elapsed_time(e1))

@@ -84,6 +84,20 @@ int arcb200_numerov_batch(int device, void *stream, int32_t nstates,
                           double *d_norm, int32_t *d_dp, int32_t normalise,
                           int32_t *d_status);
 
+/* Coefficient-array variant for NumerovBack (alkali_atom_functions.py:3939-4063, the pure-Python
+ * twin that takes an arbitrary callable kfun): the host evaluates kfun on the grid and passes, per
+ * state and grid index i (packed at d_offsets[s] + i, i < d_lengths[s]),
+ *   A_i = 2(1 - 5/12 h^2 kfun(x_i)),  B_i = 1 + h^2/12 kfun(x_i + h),  D_i = 1 + h^2/12 kfun(x_i - h);
+ * the kernel runs sol[i] = (A_i sol[i+1] - B_i sol[i+2]) / D_i from i = L-1 down (x_{L-1} =
+ * d_xtop[s], x_{i-1} = x_i - h) with the twin's divergence control and tail rule.
+ * d_inits = double[nstates][2] = {init1, init2}.  Outputs unnormalised: d_psi = sol*sqrt(x),
+ * d_r = x^2; d_dp = divergencePoint; d_status as in arcb200_numerov_batch. */
+int arcb200_numerov_coeff_batch(int device, void *stream, int32_t nstates,
+                                const int64_t *d_offsets, const int32_t *d_lengths,
+                                const double *d_A, const double *d_B, const double *d_D,
+                                const double *d_xtop, const double *d_step, const double *d_inits,
+                                double *d_psi, double *d_r, int32_t *d_dp, int32_t *d_status);
+
 /* Batched radial overlap integrals, one warp per pair:
  *   out[p] = trapezoid(psi_a*psi_b*r_a^power, x=r_a)[0:min(La,Lb)]
  * replaces the integration in AlkaliAtom.getRadialMatrixElement

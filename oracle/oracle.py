@@ -107,6 +107,60 @@ def ref_numerov(*args):
     return flat[:L].copy(), flat[L:2 * L].copy()
 
 
+def numerov_back(innerLimit, outerLimit, kfun, step, init1, init2):
+    """Restatement of the pure-Python integrator NumerovBack (aaf:3939-4063): same grid
+    (aaf:3984-3991), recurrence (aaf:3992-4019), checkPoint / divergence walk (aaf:4021-4047),
+    tail rule (aaf:4049-4054) and output conversion (aaf:4056-4060).  Pinned by
+    tests/golden/numerovback_golden.npz (outputs of the live reference)."""
+    from math import sqrt
+    br = round((sqrt(outerLimit) - sqrt(innerLimit)) / step)
+    sol = np.zeros(br)
+    rad = np.zeros(br)
+    h2 = step ** 2
+
+    def nxt(x, y1, y2):
+        return ((2.0 * (1.0 - 5.0 / 12.0 * h2 * kfun(x)) * y1 - (1.0 + 1.0 / 12.0 * h2 * kfun(x + step)) * y2)
+                / (1 + 1 / 12.0 * h2 * kfun(x - step)))
+    br -= 1
+    x = sqrt(innerLimit) + step * (br - 1)
+    sol[br] = nxt(x, init1, init2)
+    rad[br] = x
+    x -= step
+    br -= 1
+    sol[br] = nxt(x, sol[br + 1], init1)
+    rad[br] = x
+    maxValue, checkPoint, fromLastMax = 0.0, 0, 0
+    while br > checkPoint:
+        br -= 1
+        x -= step
+        sol[br] = nxt(x, sol[br + 1], sol[br + 2])
+        rad[br] = x
+        if abs(sol[br] * sqrt(x)) > maxValue:
+            maxValue = abs(sol[br] * sqrt(x))
+        else:
+            fromLastMax += 1
+            if fromLastMax > 50:
+                checkPoint = br
+    divergencePoint = 0
+    while br > 0 and divergencePoint == 0:
+        br -= 1
+        x -= step
+        sol[br] = nxt(x, sol[br + 1], sol[br + 2])
+        rad[br] = x
+        if divergencePoint == 0 and abs(sol[br] * sqrt(x)) > maxValue:
+            divergencePoint = br
+            while abs(sol[divergencePoint]) > abs(sol[divergencePoint + 1]) and divergencePoint < checkPoint:
+                divergencePoint += 1
+            if divergencePoint > checkPoint:
+                raise RuntimeError("Numerov error")
+    br = divergencePoint
+    while br > 0:
+        rad[br] = rad[br + 1] - step
+        sol[br] = 0
+        br -= 1
+    return rad * rad, sol * np.sqrt(rad), divergencePoint
+
+
 def trapezoid(y, x):
     """scipy.integrate.trapezoid(y, x=x) (aaf:34): sum(dx * (y[1:]+y[:-1]) / 2)."""
     d = np.diff(x)

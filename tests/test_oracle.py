@@ -105,3 +105,16 @@ def test_oracle_stark_matches_golden(gold_dir):
     y, hl, comp = oracle.stark_diagonalise(mat1, mat2, fields, int(g["indexOfCoupledState"]))
     np.testing.assert_allclose(y, g["y"][[0, 6, 12]], rtol=0, atol=1e-9)
     np.testing.assert_allclose(hl, g["highlight"][[0, 6, 12]], rtol=0, atol=1e-9)
+
+
+def test_oracle_numerov_back_matches_live_reference(gold_dir):
+    """Restatement of the pure-Python NumerovBack (aaf:3939-4063) against outputs of the live
+    reference for analytic callables: bit-exact, including the divergence cut."""
+    from tools.gen_golden import numerovback_cases
+    g = np.load(os.path.join(gold_dir, "numerovback_golden.npz"))
+    for name, inner, outer, k, step, i1, i2 in numerovback_cases():
+        r, psi, dp = oracle.numerov_back(inner, outer, k, step, i1, i2)
+        assert len(r) == int(g[name + "_L"])
+        assert np.array_equal(r[::7], g[name + "_r"]) and np.array_equal(psi[::7], g[name + "_psi"])
+        assert np.array_equal(psi[:400], g[name + "_head_psi"]) and np.array_equal(r[:400], g[name + "_head_r"])
+        assert float((psi == 0).sum()) == g[name + "_sum"][3]

@@ -1,0 +1,299 @@
+"""Round-2 GPU parity tests: BASELINE configs C4 and C5 at their STATED size against the live
+reference (goldens frozen by tools/gen_golden.py c4singlet / c4triplet / c5), the full C2 table
+Gram-vs-per-pair, NumerovBack with arbitrary callables, full composition (upTo=-1),
+StarkMap.getState, sorted eigenvectors on an odd number of points, per-state Numerov status.
+Tolerances (BASELINE.json north_star): energies 1e-9 relative to the spectral scale, matrix
+elements 1e-8 relative, highlight 1e-6."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dense_mat2(g):
+    N = len(g["mat1_diag"])
+    m = np.zeros((N, N))
+    m[g["mat2_rows"], g["mat2_cols"]] = g["mat2_vals"]
+    return m
+
+
+def _cluster_sums(y, h, tol):
+    cid = np.concatenate([[0], np.cumsum(np.diff(y) > tol)])
+    return np.bincount(cid, weights=h)
+
+
+# ------------------------------------------------------------------------------ C4 at full size
+@pytest.mark.parametrize("name,N", [("stark_c4_singlet_golden.npz", 651),
+                                    ("stark_c4_triplet_golden.npz", 1932)])
+def test_c4_sr88_full_size_matches_reference(gold_dir, name, N):
+    """BASELINE configs[3]: Sr88 n=50-70, lmax=30; singlet N=651 (one-stage path), triplet
+    N=1932 (two-stage path, includes the unphysical 3S0 state the reference admits)."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, name))
+    calc = arc_b200.StarkMap(arc_b200.Strontium88())
+    a = g["args"]
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]),
+                     s=float(g["s"]))
+    assert len(calc.basisStates) == N == len(g["basisStates"])
+    assert np.allclose(np.array(calc.basisStates), g["basisStates"])
+    assert calc.indexOfCoupledState == int(g["indexOfCoupledState"])
+    d = np.diag(calc.mat1)
+    assert np.abs(d - g["mat1_diag"]).max() <= 1e-12 * np.abs(d).max()
+    m2 = _dense_mat2(g)
+    nz = m2 != 0
+    assert np.array_equal(calc.mat2 != 0, nz)
+    assert np.abs(calc.mat2[nz] / m2[nz] - 1).max() <= 1e-8          # matrix elements
+    calc.diagonalise(g["fields"])
+    y, hl = np.array(calc.y), np.array(calc.highlight)
+    scale = np.abs(g["y"]).max()
+    assert np.abs(y - g["y"]).max() <= 1e-9 * scale
+    for f in range(len(g["fields"])):
+        A = _cluster_sums(g["y"][f], hl[f], 1e-7 * scale)
+        B = _cluster_sums(g["y"][f], g["highlight"][f], 1e-7 * scale)
+        assert np.abs(A - B).max() <= 1e-6, f
+
+
+# ------------------------------------------------------------------------------ C5 at full size
+def test_c5_full_size_matches_reference(gold_dir):
+    """BASELINE configs[4]: Rb 80D5/2+80D5/2, theta=pi/4, Bz=1e-4 T, nRange=3, lrange=4, 10 GHz:
+    272 channels, N=10384.  Operators against the reference's defineBasis (904 s there), two R
+    points against its eigsh output and against LAPACK on the reference's own matrices."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "pair_c5_golden.npz"))
+    c, b = g["ctor"], g["basis"]
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]))
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]), Bz=float(b[5]))
+    assert len(calc.channel) == len(g["channel"]) == 272
+    assert len(calc.basisStates) == 10384
+    assert np.allclose(np.array(calc.channel)[:, :6], g["channel"][:, :6])
+    assert np.allclose(np.array(calc.basisStates), g["basisStates"])
+    assert np.array_equal(calc.index, g["index"])
+    assert calc.originalPairStateIndex == int(g["originalPairStateIndex"])
+    d = calc.matDiagonal.diagonal()
+    assert np.abs(d - g["matDiagonal"]).max() <= 1e-9 * np.abs(d).max()
+    assert calc.matR[0].nnz == int(g["matR0_nnz"])
+    ref = g["matR0_probe"]
+    assert np.abs(calc.matR[0].dot(g["probes"]) - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert abs(abs(calc.matR[0]).sum() - float(g["matR0_sumabs"])) <= 1e-8 * float(g["matR0_sumabs"])
+    k = int(g["k"])
+    calc.diagonalise(g["r"], k)
+    assert np.array_equal(np.asarray(calc.r), g["r"])
+    y, hl = np.array(calc.y), np.array(calc.highlight)
+    scale = max(np.abs(g["y_dense"]).max(), 1e-3)
+    assert np.abs(y - g["y_dense"]).max() <= 1e-9 * scale          # LAPACK on the reference's matrices
+    assert np.abs(y - g["y"]).max() <= 1e-6 * scale                # eigsh itself (tol=1e-6)
+    for i in range(len(g["r"])):
+        A = _cluster_sums(g["y_dense"][i], hl[i], 1e-6 * scale)
+        B = _cluster_sums(g["y_dense"][i], g["highlight"][i], 1e-6 * scale)
+        assert np.abs(A[1:-1] - B[1:-1]).max() <= 1e-6, i
+
+
+# ------------------------------------------------------------------------------ C2: the whole table
+def test_c2_full_table_gram_vs_per_pair():
+    """All 1 587 317 elements of BASELINE configs[1]: the tensor-core Gram path (with its
+    refinement of cancelling elements) against the exact per-pair kernel, 1e-8 relative."""
+    import arc_b200
+    from arc_b200 import radial
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from dev_radial_bench import c2_blocks
+    atom = arc_b200.Rubidium()
+    states, blocks, nel = c2_blocks(atom)
+    assert nel == 1587317 and len(states) == 4139
+    recs = np.array([atom._state_record(*s) for s in states])
+    rb = radial.RadialBatch(recs)
+    assert not rb.status().any()
+    out, offs, nref = rb.gram_refined_device(blocks, thresh=radial.GRAM_REFINE_THRESH)
+    out = out.cpu().numpy()
+    E = recs["stateEnergy"]
+    worst, checked = 0.0, 0
+    for gi, (A, B, p) in enumerate(blocks):
+        A, B = np.asarray(A), np.asarray(B)
+        a, b = np.meshgrid(A, B, indexing="ij")
+        a, b = a.ravel(), b.ravel()
+        swap = E[a] > E[b]
+        lo, hi = np.where(swap, b, a), np.where(swap, a, b)
+        ref = rb.integrals(np.stack([lo, hi, np.full_like(lo, p)], 1).astype(np.int32))
+        got = out[offs[gi]:offs[gi] + len(ref)]
+        nzr = ref != 0
+        worst = max(worst, float(np.abs(got[nzr] / ref[nzr] - 1).max()))
+        checked += len(ref)
+    assert checked >= nel
+    assert worst <= 1e-8, worst
+
+
+# ------------------------------------------------------------------------------ NumerovBack
+def test_numerov_back_arbitrary_callable_matches_reference(gold_dir):
+    """NumerovBack (alkali_atom_functions.py:3939-4063) with arbitrary Python callables: against
+    outputs of the live reference and the oracle restatement (same IEEE operations: 1e-13)."""
+    import arc_b200
+    from oracle import oracle
+    from tools.gen_golden import numerovback_cases
+    g = np.load(os.path.join(gold_dir, "numerovback_golden.npz"))
+    for name, inner, outer, k, step, i1, i2 in numerovback_cases():
+        r, psi = arc_b200.NumerovBack(inner, outer, k, step, i1, i2)
+        assert len(r) == int(g[name + "_L"])
+        sc = np.abs(g[name + "_psi"]).max()
+        assert np.abs(r[::7] - g[name + "_r"]).max() <= 1e-13 * np.abs(g[name + "_r"]).max(), name
+        assert np.abs(psi[::7] - g[name + "_psi"]).max() <= 1e-12 * sc, name
+        assert np.abs(psi[:400] - g[name + "_head_psi"]).max() <= 1e-12 * sc, name
+        assert np.abs(r[:400] - g[name + "_head_r"]).max() <= 1e-13 * np.abs(g[name + "_r"]).max(), name
+        assert float((psi == 0).sum()) == g[name + "_sum"][3], name      # same divergence cut
+        ro, po, _dp = oracle.numerov_back(inner, outer, k, step, i1, i2)
+        assert np.abs(psi - po).max() <= 1e-12 * sc and np.abs(r - ro).max() <= 1e-13 * ro.max()
+
+
+def test_radial_wavefunction_python_route_matches_reference(gold_dir):
+    """cpp_numerov=False: the reference's pure-Python route (aaf:606-623)."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "numerovback_golden.npz"))
+    atom = arc_b200.Rubidium(cpp_numerov=False)
+    for nm in ("rb_9_0", "rb_8_2"):
+        a = g[nm + "_args"]
+        r, psi = atom.radialWavefunction(int(a[0]), a[1], a[2], a[3], a[4], a[5], a[6])
+        assert len(r) == int(g[nm + "_L"])
+        assert np.abs(r[::7] - g[nm + "_r"]).max() <= 1e-12 * g[nm + "_r"].max()
+        assert np.abs(psi[::7] - g[nm + "_psi"]).max() <= 1e-9 * np.abs(g[nm + "_psi"]).max()
+
+
+def test_numerov_status_per_state():
+    import arc_b200
+    from arc_b200 import radial
+    atom = arc_b200.Rubidium()
+    recs = np.array([atom._state_record(n, 0, .5) for n in (20, 30, 40)])
+    rb = radial.RadialBatch(recs)
+    assert rb.status().shape == (3,) and not rb.status().any()
+    rb.raise_on_failure()
+    bad = recs.copy()
+    bad["stateEnergy"][1] = np.nan                     # poisoned state: no usable norm
+    rb = radial.RadialBatch(bad)
+    st = rb.status()
+    assert st[0] == 0 and st[2] == 0 and st[1] != 0
+    with pytest.raises(RuntimeError):
+        rb.raise_on_failure()
+
+
+# ------------------------------------------------------------------------------ composition / getState
+def test_full_composition_upTo_minus_one(gold_dir):
+    """upTo=-1 (calculations_atom_single.py:1399-1407): every basis state, sorted by |c|."""
+    import arc_b200
+    from arc_b200 import sweep
+    g = np.load(os.path.join(gold_dir, "stark_small_bz_golden.npz"))
+    N = len(g["mat1_diag"])
+    V = _dense_mat2(g)
+    F = g["fields"][[1, 3]]
+    res = sweep.stark_sweep(g["mat1_diag"], V, F, int(g["indexOfCoupledState"]), topk=N, contrib_max=2.0)
+    assert res.comp_c.shape == (2, N, N)
+    for f in range(2):
+        w, v = np.linalg.eigh(np.diag(g["mat1_diag"]) + V * F[f])
+        for i in (0, N // 2, N - 1):
+            c, ix = res.comp_c[f, i], res.comp_i[f, i]
+            assert sorted(ix.tolist()) == list(range(N))                  # a permutation of the basis
+            assert np.all(np.diff(np.abs(c)) <= 1e-15)                    # descending |c|
+            sgn = np.sign(np.dot(c, v[ix, i]))
+            assert np.abs(c - sgn * v[ix, i]).max() <= 1e-9
+    # through the public API, and an intermediate upTo > 9
+    calc = arc_b200.StarkMap(arc_b200.Rubidium())
+    a = g["args"]
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]),
+                     Bz=float(g["Bz"]))
+    calc.diagonalise(F, upTo=-1)
+    comp = calc.composition[1][5]
+    assert len(comp) == N and abs(sum(cc[0] ** 2 for cc in comp) - 1.0) < 1e-9
+    calc.diagonalise(F, upTo=13, totalContributionMax=0.999999)
+    comp = calc.composition[1][5]
+    assert 1 <= len(comp) <= 12
+
+
+def test_stark_get_state():
+    """StarkMap.getState (calculations_atom_single.py:1577-1668) against numpy on the same matrices."""
+    import arc_b200
+    from scipy.constants import e as C_e, h as C_h
+    calc = arc_b200.StarkMap(arc_b200.Rubidium())
+    states, coef, energy = calc.getState([30, 0, 0.5, 0.5], 300.0, 28, 32, 6, accountForAmplitude=0.95)
+    m = calc.mat1 + calc.mat2 * 300.0
+    ev, vec = np.linalg.eigh(m)
+    i = int(np.argmax(np.abs(vec[calc.indexOfCoupledState]) ** 2))
+    assert abs(energy - ev[i] * 1e9 * C_h / C_e) <= 1e-9 * abs(energy)
+    order = np.argsort(np.abs(vec[:, i]))[::-1]
+    assert states[0] == calc.basisStates[order[0]]
+    acc, n = 0.95, 0
+    while acc > 0 and n < len(order):
+        acc -= vec[order[n], i] ** 2
+        n += 1
+    assert len(coef) == n == len(states)
+    sgn = np.sign(coef[0] * vec[order[0], i])
+    assert np.abs(np.array(coef) - sgn * vec[order[:n], i]).max() <= 1e-9
+
+
+def test_sorted_eigenvectors_odd_number_of_points(gold_dir):
+    """sortEigenvectors=True with an ODD number of R points (and odd batches): the overlap window
+    sits behind the workspace, whose size used to leave it 4-byte aligned for odd batches."""
+    import arc_b200
+    g = np.load(os.path.join(gold_dir, "pair_sorted_golden.npz"))
+    c, b = g["ctor"], g["basis"]
+    calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), int(c[0]), int(c[1]), float(c[2]), int(c[3]),
+                                          int(c[4]), float(c[5]), float(c[6]), float(c[7]))
+    calc.defineBasis(float(b[0]), float(b[1]), int(b[2]), int(b[3]), float(b[4]))
+    R = np.linspace(2.0, 8.0, 25)
+    k = int(g["k"])
+    calc.diagonalise(R, k, sortEigenvectors=True)
+    y_all = np.array(calc.y)
+    for batch in (7, 3, 25):
+        calc.diagonalise(R, k, sortEigenvectors=True, batch=batch)
+        assert np.abs(np.array(calc.y) - y_all).max() <= 1e-9 * np.abs(y_all).max()
+    calc.diagonalise(R, k)
+    assert np.abs(np.sort(y_all, axis=1) - np.array(calc.y)).max() <= 1e-9 * np.abs(y_all).max()
+
+
+# ------------------------------------------------------------------------------ multi-GPU (NCCL)
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import arc_b200
+        from arc_b200 import sweep
+        atom = arc_b200.Rubidium()
+        atom.radial_group = sweep.WORLD
+        calc = arc_b200.StarkMap(atom)
+        calc.defineBasis(30, 0, 0.5, 0.5, 28, 32, 6)
+        F = np.linspace(0, 500, 11)
+        calc.diagonalise(F, group=sweep.WORLD)
+        y_sharded = np.array(calc.y)
+        calc.diagonalise(F)                            # group=None: local, no collective
+        q.put((rank, float(np.abs(np.array(calc.y) - y_sharded).max()), y_sharded.shape))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sweep_two_gpus_nccl():
+    """Sharded defineBasis (radial table all-gather) + diagonalise over 2 ranks with NCCL; skipped
+    on a one-GPU box."""
+    import socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, err, shape in outs:
+        assert shape[0] == 11 and err == 0.0

@@ -346,6 +346,50 @@ def gen_lown(arc):
                 "stark_k_lown_golden.npz")
 
 
+def numerovback_cases():
+    """(name, inner, outer, kfun, step, init1, init2) -- analytic callables, shared by the golden
+    generator and the tests (tests/test_radial_gpu.py imports this)."""
+    from math import exp
+
+    def hyd(l, E):
+        def k(x):
+            r = x * x
+            return -3.0 / (4.0 * r) + 4.0 * r * (2.0 * (E + 1.0 / r) - l * (l + 1) / (r ** 2))
+        return k
+
+    def screened(x):          # scalar-only callable (math.exp): exercises the per-point fallback
+        r = x * x
+        return -3.0 / (4.0 * r) + 4.0 * r * (2.0 * (-0.01 + (1.0 + 5.0 * exp(-1.3 * r)) / r) - 2.0 / (r ** 2))
+    return [("hyd_10s", 0.05, 2.0 * 10 * 25, hyd(0, -0.5 / 100.0), 0.001, 0.01, 0.01),
+            ("hyd_6p", 0.01, 2.0 * 6 * 21, hyd(1, -0.5 / 36.0), 0.002, 0.01, 0.01),
+            ("hyd_offres_l2_diverging", 0.01, 2.0 * 8 * 23, hyd(2, -0.5 / 6.3 ** 2), 0.001, 0.01, 0.01),
+            ("hyd_offres_l1_diverging", 0.0025, 2.0 * 8 * 23, hyd(1, -0.5 / 5.5 ** 2), 0.001, 0.01, 0.01),
+            ("screened_7p", 0.3, 2.0 * 7 * 22, screened, 0.001, 0.01, 0.005)]
+
+
+def gen_numerovback(arc):
+    """Outputs of the live reference's pure-Python NumerovBack (aaf:3939-4063) for analytic
+    callables, and of radialWavefunction on the cpp_numerov=False path (aaf:606-623)."""
+    from arc.alkali_atom_functions import NumerovBack
+    d = {}
+    for name, inner, outer, k, step, i1, i2 in numerovback_cases():
+        r, psi = NumerovBack(inner, outer, k, step, i1, i2)
+        d[name + "_r"], d[name + "_psi"] = r[::7].copy(), psi[::7].copy()
+        d[name + "_head_r"], d[name + "_head_psi"] = r[:400].copy(), psi[:400].copy()
+        d[name + "_L"] = len(r)
+        d[name + "_sum"] = np.array([psi.sum(), np.abs(psi).sum(), r.sum(), float((psi == 0).sum())])
+        print(name, len(r), int((psi == 0).sum()))
+    a = arc.Rubidium(cpp_numerov=False)
+    for (n, l, j) in ((9, 0, 0.5), (8, 2, 2.5)):
+        E = a.getEnergy(n, l, j) / 27.211
+        r, psi = a.radialWavefunction(l, 0.5, j, E, a.alphaC ** (1 / 3.0), 2.0 * n * (n + 15.0), 0.001)
+        nm = "rb_%d_%d" % (n, l)
+        d[nm + "_r"], d[nm + "_psi"], d[nm + "_L"] = r[::7].copy(), psi[::7].copy(), len(r)
+        d[nm + "_args"] = np.array([l, 0.5, j, E, a.alphaC ** (1 / 3.0), 2.0 * n * (n + 15.0), 0.001])
+        print(nm, len(r))
+    np.savez_compressed(os.path.join(GOLD, "numerovback_golden.npz"), **d)
+
+
 def gen_c4(arc, which):
     """C4 (BASELINE.json configs[3]) at its stated size: Sr88 n=50-70, lmax=30, singlet N=651 /
     triplet N=1932; 8 of the 2000 fields kept."""
@@ -534,6 +578,8 @@ if __name__ == "__main__":
         gen_pair(arc, big=True)
     if "divalent" in what:
         gen_divalent(arc)
+    if "numerovback" in what:
+        gen_numerovback(arc)
     if "lown" in what:
         gen_lown(arc)
     if "c4singlet" in what:
