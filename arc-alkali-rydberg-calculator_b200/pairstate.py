@@ -51,6 +51,32 @@ def _coupling_order(l, j, l1, j1, upTo):
         return 2
     return 0
 
+def _unembed_hermitian(w2, v2, n):
+    """Eigenpairs of an n x n complex-Hermitian matrix from those of its 2n x 2n real symmetric
+    embedding [[Re, -Im], [Im, Re]] (w2 ascending, v2[:, i] eigenvectors): every eigenvalue of the
+    Hermitian matrix appears twice; inside each cluster of equal eigenvalues the embedded vectors
+    (x; y) -> x + i y span the complex eigenspace, an orthonormal basis of which is taken from
+    their SVD.  Returns (w[n] ascending, vecs[n, n] with vecs[i] the i-th eigenvector)."""
+    z = v2[:n, :] + 1j * v2[n:, :]
+    scale = max(np.abs(w2).max(), 1e-300)
+    w, vecs = [], []
+    a = 0
+    while a < 2 * n:
+        b = a + 1
+        while b < 2 * n and abs(w2[b] - w2[a]) <= 1e-10 * scale:
+            b += 1
+        d = (b - a) // 2
+        u, _s, _vh = np.linalg.svd(z[:, a:b], full_matrices=False)
+        for q in range(d):
+            w.append(float(np.mean(w2[a:b])))
+            vecs.append(u[:, q])
+        a = b
+    if len(w) != n:          # a cluster was split by the tolerance: plain pairing of the doubled spectrum
+        w = [float(0.5 * (w2[2 * i] + w2[2 * i + 1])) for i in range(n)]
+        q, _r = np.linalg.qr(z[:, ::2])
+        vecs = list(q.T)
+    return np.array(w), np.array(vecs)
+
 
 class PairCompositionView:
     """Lazy `composition[r][i]` -> LaTeX string of the <= 4 dominant basis states, as
@@ -309,6 +335,196 @@ class PairStateInteractions:
                     return value[i]
             return float(state.dot(inter.dot(state)))
         return np.real(value), vectors
+
+    # ------------------------------------------------------------------ C6 on (theta, phi) grids
+    def _ljCoupledCheck(self, l, j, l1, j1, s):
+        """Is (l, j) -> (l1, j1) dipole (or, with interactionsUpTo = 2, quadrupole) coupled?
+        Selection rules of calculations_atom_pairstate.py:1490-1547, including its use of
+        Python's round-half-even (`round(j - 0.5)` is 0 for j = 1/2 AND for j = 1)."""
+        if (l == l1 and j == j1) or (abs(j) < 0.1 and abs(j1) < 0.1) or (abs(l) < 0.1 and abs(l1) < 0.1):
+            return False
+        if not (abs(round(l - j)) < s + 0.1 and abs(round(l1 - j1)) < s + 0.1):
+            return False
+        dl, dj = abs(round(l - l1)), abs(round(j - j1))
+        if dl == 1 and dj in (0, 1):
+            return True
+        if self.interactionsUpTo != 2 or dl not in (0, 2) or dj not in (0, 1, 2):
+            return False
+
+        def is0(x):
+            return abs(x) < 0.1
+        forbidden = ((is0(j) and is0(round(j1 - 1))) or (is0(round(j - 1)) and is0(j1))
+                     or (is0(round(j - 0.5)) and is0(round(j1 - 0.5)))
+                     or (is0(l) and is0(round(l1 - 1))) or (is0(round(l - 1)) and is0(l1)))
+        return not forbidden
+
+    def _findAllCoupledAngularMomentumStates(self, l, j, s1, ll, jj, s2, stateHopping=False):
+        """All second-order paths (l,j; ll,jj) -> (l1,j1; l2,j2) -> final, final = initial or,
+        for state hopping, the swapped pair (calculations_atom_pairstate.py:1549-1639); tuples
+        (l, j, ll, jj, l1, j1, l2, j2, l', j', ll', jj') in the reference's loop order."""
+        up = self.interactionsUpTo
+        legs1 = [(l1, float(j1)) for l1 in range(max(0, l - up), l + up + 1)
+                 for j1 in np.arange(max(s1, j - up), j + up + 1, 1) if self._ljCoupledCheck(l, j, l1, j1, s1)]
+        legs2 = [(l2, float(j2)) for l2 in range(max(0, ll - up), ll + up + 1)
+                 for j2 in np.arange(max(s2, jj - up), jj + up + 1, 1) if self._ljCoupledCheck(ll, jj, l2, j2, s2)]
+        out = []
+        for l1, j1 in legs1:
+            for l2, j2 in legs2:
+                if not stateHopping:
+                    out.append((l, j, ll, jj, l1, j1, l2, j2, l, j, ll, jj))
+                elif self._ljCoupledCheck(l1, j1, ll, jj, s1) and self._ljCoupledCheck(l2, j2, l, j, s2):
+                    out.append((l, j, ll, jj, l1, j1, l2, j2, ll, jj, l, j))
+        return out
+
+    def _getC6contributions_lj(self, nRange, energyDelta, stateHopping=False):
+        """Per angular path the radial sum V_lj = sum_{n', n''} |V1 V2| / defect in GHz um^6
+        (calculations_atom_pairstate.py:1641-1789).  All radial elements of all paths are
+        computed in ONE batched GPU run per atom before the sums are formed."""
+        paths = self._findAllCoupledAngularMomentumStates(self.l, self.j, self.s1, self.ll, self.jj, self.s2,
+                                                          stateHopping=stateHopping)
+        n1s = range(max(self.n - nRange, 1), self.n + nRange + 1)
+        n2s = range(max(self.nn - nRange, 1), self.nn + nRange + 1)
+        a1, a2 = self.atom1, self.atom2
+        ok_hop = (not stateHopping) or (self.nn >= a1.groundStateN and self.n >= a2.groundStateN)
+        terms = []                     # (path index, n', n'', defect)
+        for pi_, (l, j, ll, jj, l2, j2, ll2, jj2, l3, j3, ll3, jj3) in enumerate(paths):
+            for n2 in n1s:
+                for nn2 in n2s:
+                    # like the reference, `[n, l, j] in extraLevels` compares a list with tuples
+                    nCheck = ((n2 >= a1.groundStateN or [n2, l2, j2] in a1.extraLevels)
+                              and (nn2 >= a2.groundStateN or [nn2, ll2, jj2] in a2.extraLevels) and ok_hop)
+                    defect = self._getEnergyDefect(self.n, l, j, self.nn, ll, jj, n2, l2, j2, nn2, ll2, jj2) \
+                        / C_h * 1e-9
+                    if abs(defect) < 1e-10:
+                        raise ValueError("The requested pair-state is dipole coupled resonatly (energy "
+                                         "defect = 0) to other pair-states. Aborting pertubative calculation.")
+                    if abs(defect) < energyDelta * 10 ** -9 and nCheck:
+                        terms.append((pi_, n2, nn2, defect))
+        # batch seam: every leg of every term, per atom
+        want = {id(a1): ([], [], a1, self.s1), id(a2): ([], [], a2, self.s2)}
+
+        def need(atom, sa, sb):
+            order = 1 if (abs(sa[1] - sb[1]) == 1 and abs(sa[2] - sb[2]) < 1.1) else 2
+            want[id(atom)][order - 1].append(tuple(sa) + tuple(sb))
+        for pi_, n2, nn2, _d in terms:
+            l, j, ll, jj, l2, j2, ll2, jj2, l3, j3, ll3, jj3 = paths[pi_]
+            need(a1, (self.n, l, j), (n2, l2, j2))
+            need(a2, (self.nn, ll, jj), (nn2, ll2, jj2))
+            if stateHopping:
+                need(a1, (n2, l2, j2), (self.nn, l3, j3))
+                need(a2, (nn2, ll2, jj2), (self.n, ll3, jj3))
+        for dip, quad, atom, spin in want.values():
+            before = atom.gpu_kernel_launches
+            if getattr(atom, "divalent", False):
+                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad, s=spin)
+            else:
+                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad)
+            self.gpu_kernel_launches += atom.gpu_kernel_launches - before
+        a0 = physical_constants["Bohr radius"][0]
+        unit = 1.0e-9 * (1.0e6) ** 3 / C_h                                    # J m^3 -> GHz um^3
+
+        def strength(sa1, sb1, sa2, sb2):
+            """_atomLightAtomCoupling (alkali_atom_functions.py:4066-4130) in GHz um^3."""
+            c = 0
+            for (x, y) in ((sa1, sb1), (sa2, sb2)):
+                c += 1 if (abs(x[1] - y[1]) == 1 and abs(x[2] - y[2]) < 1.1) else 2
+            r1 = a1.getRadialCoupling(*sa1, *sb1, s=self.s1)
+            r2 = a2.getRadialCoupling(*sa2, *sb2, s=self.s2)
+            return C_e ** 2 / (4.0 * pi * epsilon_0) * r1 * r2 * a0 ** c * unit
+        V = [0.0] * len(paths)
+        for pi_, n2, nn2, defect in terms:
+            l, j, ll, jj, l2, j2, ll2, jj2, l3, j3, ll3, jj3 = paths[pi_]
+            v1 = strength((self.n, l, j), (n2, l2, j2), (self.nn, ll, jj), (nn2, ll2, jj2))
+            v2 = v1 if not stateHopping else strength((n2, l2, j2), (self.nn, l3, j3),
+                                                      (nn2, ll2, jj2), (self.n, ll3, jj3))
+            V[pi_] += abs(v1 * v2) / defect
+        return [[*pth, float(v)] for pth, v in zip(paths, V)]
+
+    def _getPerturbativeC6Matrix_lj(self, ljInteractions):
+        """m_j-resolved interaction matrix sum_paths V_lj d2 d1 (calculations_atom_pairstate.py:1791-1818)."""
+        Imat = 0
+        for vals in ljInteractions:
+            d1 = self._getAngularMatrix_M(*vals[0:8])
+            d2 = self._getAngularMatrix_M(*vals[4:12])
+            Imat = Imat + vals[-1] * d2.dot(d1)
+        return np.array(Imat)
+
+    @staticmethod
+    def _getAngularBasisRotationMatrix(j1, j2):
+        """Permutation between the |m_j1> x |m_j2> and |m_j2> x |m_j1> product bases
+        (calculations_atom_pairstate.py:1462-1488)."""
+        d1, d2 = round(2 * j1 + 1), round(2 * j2 + 1)
+        P = np.zeros((d1 * d2, d1 * d2), dtype=np.complex128)
+        for i in range(d2):
+            for jx in range(d1):
+                P[i * d1 + jx, jx * d2 + i] = 1.0
+        return P
+
+    def getC6perturbatively_anglePairs(self, anglePairs, nRange, energyDelta, degeneratePerturbation=False,
+                                       returnInteractionMatrix=False):
+        """Second-order C6 (GHz um^6) for a list of (theta, phi) orientations
+        (calculations_atom_pairstate.py:2065-2287): the radial sums and the m_j-resolved interaction
+        matrices are formed once, rotated per orientation with Wigner D matrices, and -- for
+        degeneratePerturbation=True -- ALL orientations are diagonalised in one batched GPU
+        eigensolve.  phi != 0 gives complex-Hermitian matrices; they are solved through the real
+        symmetric embedding [[Re, -Im], [Im, Re]] (each eigenvalue appears twice; one complex
+        eigenvector is rebuilt per eigenvalue).  Return values as in the reference."""
+        state1 = [self.n, self.l, self.j, self.s1]
+        state2 = [self.nn, self.ll, self.jj, self.s2]
+        same = state1 == state2
+        C6, C6hop, eigenvectors, matrices = [], [], [], []
+        degenerateStates = [[self.n, self.l, self.j, self.nn, self.ll, self.jj],
+                            [self.nn, self.ll, self.jj, self.n, self.l, self.j]]
+        Imat11 = self._getPerturbativeC6Matrix_lj(self._getC6contributions_lj(nRange, energyDelta, False))
+        if not same:
+            Imat21 = self._getPerturbativeC6Matrix_lj(self._getC6contributions_lj(nRange, energyDelta, True))
+            B12 = self._getAngularBasisRotationMatrix(self.jj, self.j)
+        d2 = round(2 * self.jj + 1)
+        i1 = round(self.j + self.m1) * d2 + round(self.jj + self.m2)                  # |j m1> x |jj m2>
+        i2 = round(self.jj + self.m2) * round(2 * self.j + 1) + round(self.j + self.m1)
+        full = []
+        for angle1, angle2 in anglePairs:
+            wgd = WignerDmatrix(angle1, angle2)
+            R1 = np.kron(wgd.get(self.j), wgd.get(self.jj))
+            I11 = R1.dot(Imat11.dot(R1.conj().T))
+            if not same:
+                R2 = np.kron(wgd.get(self.jj), wgd.get(self.j))
+                I21 = R2.dot(Imat21.dot(R1.conj().T))
+            if not degeneratePerturbation:
+                C6.append(float(np.real(I11[i1, i1])))
+                if not same:
+                    C6hop.append(float(np.real(I21[i2, i1])))
+            if degeneratePerturbation or returnInteractionMatrix:
+                Irot = I11 if same else np.block([[I11, B12.dot(I21.dot(B12))],
+                                                  [I21, B12.T.dot(I11.dot(B12))]])
+                full.append(np.array(Irot))
+                if returnInteractionMatrix:
+                    matrices.append(np.array(Irot))
+        if degeneratePerturbation:
+            # numpy.linalg.eigh reads the lower triangle only: make that explicit, then one batch
+            herm = [np.tril(M) + np.tril(M, -1).conj().T for M in full]
+            cplx = any(np.abs(M.imag).max() > 0 for M in herm)
+            if not cplx:
+                w, v = _sweep.syevd_batched(np.stack([M.real for M in herm]),
+                                            device=getattr(self.atom1, "device", None))
+                for t in range(len(herm)):
+                    C6.append(np.array(w[t]))
+                    eigenvectors.append(np.array(v[t].T, dtype=np.complex128))
+            else:
+                emb = np.stack([np.block([[M.real, -M.imag], [M.imag, M.real]]) for M in herm])
+                w, v = _sweep.syevd_batched(emb, device=getattr(self.atom1, "device", None))
+                for t, M in enumerate(herm):
+                    ev, vecs = _unembed_hermitian(w[t], v[t], M.shape[0])
+                    C6.append(ev)
+                    eigenvectors.append(vecs)
+            self.gpu_kernel_launches += 1
+        if not degeneratePerturbation and not returnInteractionMatrix:
+            return C6, C6hop
+        if not degeneratePerturbation:
+            return C6, C6hop, matrices
+        if not returnInteractionMatrix:
+            return C6, eigenvectors, degenerateStates
+        return C6, eigenvectors, matrices, degenerateStates
 
     # ------------------------------------------------------------------ channels
     def _makeRawMatrix2(self, n, l, j, nn, ll, jj, k, lrange, limit, limitBasisToMj,

@@ -53,3 +53,25 @@ def test_phi_nonzero_rejected():
     calc = arc_b200.PairStateInteractions(arc_b200.Rubidium(), 60, 0, .5, 60, 0, .5, .5, .5)
     with pytest.raises(NotImplementedError):
         calc.defineBasis(0.3, 0.2, 1, 2, 1e9)
+
+
+def test_c6_angle_pairs_host_logic(gold_dir):
+    """getC6perturbatively_anglePairs (calculations_atom_pairstate.py:2065-2287), the part that
+    needs no eigensolve: angular paths, radial sums, rotated interaction matrices, C6 and hopping
+    C6 against the live reference (radial elements from the oracle here)."""
+    import arc_b200
+    from tools.gen_golden import anglepairs_cases
+    g = np.load(os.path.join(gold_dir, "anglepairs_golden.npz"))
+    atom = patch_atom_with_oracle(arc_b200.Rubidium())
+    for name, ctor, angles, nRange, dE in anglepairs_cases():
+        calc = arc_b200.PairStateInteractions(atom, *ctor)
+        c6, c6hop, mats = calc.getC6perturbatively_anglePairs(angles, nRange, dE, returnInteractionMatrix=True)
+        ref = g[name + "_c6"]
+        assert np.abs(np.array(c6) - ref).max() <= 1e-7 * np.abs(ref).max(), name
+        assert len(c6hop) == len(g[name + "_c6hop"])
+        if len(c6hop):
+            rh = g[name + "_c6hop"]
+            assert np.abs(np.array(c6hop) - rh).max() <= 1e-7 * max(np.abs(rh).max(), np.abs(ref).max()), name
+        rm = g[name + "_mats"]
+        assert np.array(mats).shape == rm.shape
+        assert np.abs(np.array(mats) - rm).max() <= 1e-7 * np.abs(rm).max(), name

@@ -390,6 +390,33 @@ def gen_numerovback(arc):
     np.savez_compressed(os.path.join(GOLD, "numerovback_golden.npz"), **d)
 
 
+def anglepairs_cases():
+    """(name, ctor args, anglePairs, nRange, energyDelta) shared by generator and tests."""
+    return [("dd_same", (40, 2, 2.5, 40, 2, 2.5, 2.5, 2.5), [(0.0, 0.0), (np.pi / 4, 0.0), (np.pi / 2, 0.0), (1.0, 0.0)],
+             3, 30e9),
+            ("ss_diff_n", (40, 0, 0.5, 41, 0, 0.5, 0.5, -0.5), [(0.3, 0.0), (1.2, 0.0)], 3, 30e9),
+            ("pp_phi", (38, 1, 1.5, 38, 1, 1.5, 1.5, 0.5), [(0.7, 1.1), (0.2, -0.4)], 2, 25e9),
+            ("sd_diff_phi", (42, 0, 0.5, 41, 2, 1.5, 0.5, 1.5), [(0.9, 0.6)], 2, 25e9)]
+
+
+def gen_anglepairs(arc):
+    """getC6perturbatively_anglePairs (pair:2065-2287) of the live reference."""
+    a = arc.Rubidium()
+    d = {}
+    for name, ctor, angles, nRange, dE in anglepairs_cases():
+        calc = arc.PairStateInteractions(a, *ctor)
+        c6, c6hop, mats = calc.getC6perturbatively_anglePairs(angles, nRange, dE, returnInteractionMatrix=True)
+        d[name + "_c6"] = np.array(c6, dtype=float)
+        d[name + "_c6hop"] = np.array(c6hop, dtype=float)
+        d[name + "_mats"] = np.array(mats)
+        ev, vecs, deg = calc.getC6perturbatively_anglePairs(angles, nRange, dE, degeneratePerturbation=True)
+        d[name + "_ev"] = np.array(ev, dtype=float)
+        d[name + "_vecs"] = np.array(vecs)
+        d[name + "_deg"] = np.array(deg, dtype=float)
+        print(name, np.array(c6), np.array(c6hop), np.array(ev).shape)
+    np.savez_compressed(os.path.join(GOLD, "anglepairs_golden.npz"), **d)
+
+
 def gen_c4(arc, which):
     """C4 (BASELINE.json configs[3]) at its stated size: Sr88 n=50-70, lmax=30, singlet N=651 /
     triplet N=1932; 8 of the 2000 fields kept."""
@@ -578,6 +605,8 @@ if __name__ == "__main__":
         gen_pair(arc, big=True)
     if "divalent" in what:
         gen_divalent(arc)
+    if "anglepairs" in what:
+        gen_anglepairs(arc)
     if "numerovback" in what:
         gen_numerovback(arc)
     if "lown" in what:
