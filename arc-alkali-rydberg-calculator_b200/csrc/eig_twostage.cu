@@ -38,37 +38,55 @@ using namespace ts;
 // ------------------------------------------------------------------------------------------
 // stage 1: dense -> band
 // ------------------------------------------------------------------------------------------
-// WARPS = 8: one CTA per SM; WARPS = 4: two CTAs (two matrices) per SM, whose latency-bound
-// panel factorisations and tensor-bound updates overlap.
+// The five phases of a panel step are device functions shared by the kernels below (and, phase by
+// phase, by the many-CTA variant in eig_sy2sb_multi.cu's per-phase kernels): panel QR, T factor,
+// symmetric product X = A22 V, W, rank-2k update.
+constexpr int S1_TSTR = 36;      // per-warp transit tile [cc][TSTR] (column-major): conflict-free LDS.64
+                                 // fragments in both orientations
+
+struct S1Ctx {
+    int tid, wid, lane, grp, tig;
+    int np, lda, NB;
+    double *A, *Wp, *Vp, *tt, *Tfac;
+    double(*Bs)[2][32][BSTR];     // operand tiles [buf][op][n][k]
+    double(*Ts)[33];
+    double(*G)[33];
+    double(*M1)[33];
+    double(*wv)[32];
+    double(*sred)[16];
+    double *taus;
+    double *Tw;                   // this warp's two transit tiles
+};
+
+// Householder QR of the panel below the band (in place) + clean V panel
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
+__device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
 {
+    const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
+    const int np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *__restrict__ tt = c.tt;
+    double *__restrict__ Tfac = c.Tfac;
+    double(*Bs)[2][32][BSTR] = c.Bs;
+    double(*Ts)[33] = c.Ts;
+    double(*G)[33] = c.G;
+    double(*M1)[33] = c.M1;
+    double(*wv)[32] = c.wv;
+    double(*sred)[16] = c.sred;
+    double *taus = c.taus;
+    double *Tw = c.Tw;
     constexpr int NT = WARPS * 32;
-    constexpr int TSTR = 36;                         // per-warp transit tile [cc][TSTR] (column-major):
-                                                     // conflict-free LDS.64 fragments in both orientations
-    constexpr int UNI = 2 * WARPS * 32 * TSTR + 4608;   // 2 transit tiles per warp + operand tiles (doubles)
-    const int mat = blockIdx.x;
-    const int np = a.Npad, lda = a.Npad, NB = a.NB;
-    double *slot = a.base + (size_t)mat * a.slot;
-    double *A = slot + a.oA;
-    double *__restrict__ Wp = slot + a.oWp;     // [32][np] column-major: X, then W
-    double *__restrict__ Vp = slot + a.oVp;     // [32][np] clean V (explicit unit diagonal)
-    double *__restrict__ tt = slot + a.oTau;
-    double *__restrict__ Tfac = slot + a.oTfac;
-
-    extern __shared__ double sm[];
-    double *uni = sm;
-    double(*Bs)[2][32][BSTR] = reinterpret_cast<double(*)[2][32][BSTR]>(uni + 2 * WARPS * 32 * TSTR);   // [buf][op][n][k]
-    double(*Ts)[33] = reinterpret_cast<double(*)[33]>(sm + UNI);
-    double(*G)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
-    double(*M1)[33] = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
-    double(*wv)[32] = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056);          // [par][j]
-    double(*sred)[16] = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 64);   // [par][warp], [par][15] = alpha
-    double *taus = sm + UNI + 3 * 1056 + 96;                                         // [32]
-
-    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int grp = lane >> 2, tig = lane & 3;
-    double *Tw = uni + wid * (2 * 32 * TSTR);          // two transit tiles per warp
+    constexpr int TSTR = S1_TSTR;
+    const int m0 = 32 * (p + 1), col0 = 32 * p;
+    const int nch = NB - (p + 1);
+    double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
+    const int Jt = p + 1;
+    constexpr int SV = 32 / WARPS;
+    (void)tid; (void)grp; (void)tig; (void)np; (void)Wp; (void)Vp; (void)tt; (void)Tfac; (void)Bs; (void)Ts; (void)G;
+    (void)M1; (void)wv; (void)sred; (void)taus; (void)Tw; (void)NT; (void)m0; (void)col0; (void)nch; (void)P; (void)Jt;
+    (void)SV; (void)lane; (void)wid; (void)lda; (void)NB; (void)A;
     // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
     // tile: 16-byte pieces, whole 256-byte column segments per half warp
     auto issue_tile = [&](int Ib, int Jb, int tb) {
@@ -84,494 +102,943 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
             dst += 2 * TSTR;
         }
     };
-
-    TSP_DECL
-    for (int p = 0; p < NB - 1; ++p) {
-        TSP(0)
-        const int m0 = 32 * (p + 1), col0 = 32 * p;
-        const int nch = NB - (p + 1);
-        double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
-
-        // ---------------------------------------------------------------- panel QR
-        // Two phases per column c (c = -1: gather only), lane <-> row everywhere:
-        //   A  rows dealt to the warps: finalise column c (v = x * scale, beta on the diagonal),
-        //      apply H_c to column cn = c + 1 and gather its norm and pivot  -> block reduce
-        //   B  columns dealt to the warps (j = wid + WARPS k): apply H_c to the own columns j > cn
-        //      and gather g_j = sum_{r > rd+1} x_cn(r) x_j(r) and the pivot row, so that
-        //      tau' w'_j = tau' (x_j(rd+1) + scale' g_j) is known to the owner without another pass.
-        // Loads are issued in register batches ahead of the dependent stores.
-        {
-            constexpr int KO = 32 / WARPS;
-            double wreg[KO];
+    (void)issue_tile;
+    // ---------------------------------------------------------------- panel QR
+    // Two phases per column c (c = -1: gather only), lane <-> row everywhere:
+    //   A  rows dealt to the warps: finalise column c (v = x * scale, beta on the diagonal),
+    //      apply H_c to column cn = c + 1 and gather its norm and pivot  -> block reduce
+    //   B  columns dealt to the warps (j = wid + WARPS k): apply H_c to the own columns j > cn
+    //      and gather g_j = sum_{r > rd+1} x_cn(r) x_j(r) and the pivot row, so that
+    //      tau' w'_j = tau' (x_j(rd+1) + scale' g_j) is known to the owner without another pass.
+    // Loads are issued in register batches ahead of the dependent stores.
+    {
+        constexpr int KO = 32 / WARPS;
+        double wreg[KO];
 #pragma unroll
-            for (int k = 0; k < KO; ++k) wreg[k] = 0.0;
-            double tau = 0.0, scale = 0.0, beta = 0.0;
-            for (int c = -1; c < 32; ++c) {
-                const int rd = m0 + c, cn = c + 1, par = cn & 1;
-                // ---------------- phase A
-                double ssq = 0.0;
-                const double wcn = (c >= 0 && cn < 32) ? wv[c & 1][cn] : 0.0;
-                for (int ch0 = wid; ch0 < nch; ch0 += WARPS * 4) {
-                    double pc[4], pn[4];
+        for (int k = 0; k < KO; ++k) wreg[k] = 0.0;
+        double tau = 0.0, scale = 0.0, beta = 0.0;
+        for (int c = -1; c < 32; ++c) {
+            const int rd = m0 + c, cn = c + 1, par = cn & 1;
+            // ---------------- phase A
+            double ssq = 0.0;
+            const double wcn = (c >= 0 && cn < 32) ? wv[c & 1][cn] : 0.0;
+            for (int ch0 = wid; ch0 < nch; ch0 += WARPS * 4) {
+                double pc[4], pn[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
-                        pc[u] = (c >= 0 && ch < nch) ? P[r + (size_t)c * lda] : 0.0;
-                        pn[u] = (cn < 32 && ch < nch) ? P[r + (size_t)cn * lda] : 0.0;
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
+                    pc[u] = (c >= 0 && ch < nch) ? P[r + (size_t)c * lda] : 0.0;
+                    pn[u] = (cn < 32 && ch < nch) ? P[r + (size_t)cn * lda] : 0.0;
+                }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
-                        if (ch < nch) {
-                            double v = 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
+                    if (ch < nch) {
+                        double v = 0.0;
+                        if (c >= 0) {
+                            if (r == rd) {
+                                v = 1.0;
+                                P[r + (size_t)c * lda] = beta;
+                            } else if (r > rd) {
+                                v = pc[u] * scale;
+                                P[r + (size_t)c * lda] = v;
+                            }
+                            Vp[(size_t)c * np + r] = v;
+                        }
+                        if (cn < 32 && r >= rd) {
+                            double x = pn[u];
                             if (c >= 0) {
-                                if (r == rd) {
-                                    v = 1.0;
-                                    P[r + (size_t)c * lda] = beta;
-                                } else if (r > rd) {
-                                    v = pc[u] * scale;
-                                    P[r + (size_t)c * lda] = v;
-                                }
-                                Vp[(size_t)c * np + r] = v;
+                                x -= v * wcn;
+                                P[r + (size_t)cn * lda] = x;
                             }
-                            if (cn < 32 && r >= rd) {
-                                double x = pn[u];
-                                if (c >= 0) {
-                                    x -= v * wcn;
-                                    P[r + (size_t)cn * lda] = x;
-                                }
-                                if (r == rd + 1) sred[par][15] = x;
-                                if (r > rd + 1) ssq += x * x;
-                            }
+                            if (r == rd + 1) sred[par][15] = x;
+                            if (r > rd + 1) ssq += x * x;
                         }
                     }
                 }
-                if (cn >= 32) break;
-                ssq = warp_sum(ssq);
-                if (lane == 0) sred[par][wid] = ssq;
-                __syncthreads();                                     // #1
-                double xn2 = 0.0;
+            }
+            if (cn >= 32) break;
+            ssq = warp_sum(ssq);
+            if (lane == 0) sred[par][wid] = ssq;
+            __syncthreads();                                     // #1
+            double xn2 = 0.0;
 #pragma unroll
-                for (int q = 0; q < WARPS; ++q) xn2 += sred[par][q];
-                const double alpha = sred[par][15];
-                double tau_n = 0.0, beta_n = alpha, scale_n = 0.0;
-                if (rd + 1 < np - 1 && xn2 != 0.0) {
-                    beta_n = -copysign(sqrt(alpha * alpha + xn2), alpha);
-                    tau_n = (beta_n - alpha) / beta_n;
-                    scale_n = 1.0 / (alpha - beta_n);
-                }
-                if (tid == 0) { tt[col0 + cn] = tau_n; taus[cn] = tau_n; }
-                // ---------------- phase B
-                double g[KO], h[KO];
+            for (int q = 0; q < WARPS; ++q) xn2 += sred[par][q];
+            const double alpha = sred[par][15];
+            double tau_n = 0.0, beta_n = alpha, scale_n = 0.0;
+            if (rd + 1 < np - 1 && xn2 != 0.0) {
+                beta_n = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                tau_n = (beta_n - alpha) / beta_n;
+                scale_n = 1.0 / (alpha - beta_n);
+            }
+            if (tid == 0) { tt[col0 + cn] = tau_n; taus[cn] = tau_n; }
+            // ---------------- phase B
+            double g[KO], h[KO];
 #pragma unroll
-                for (int k = 0; k < KO; ++k) g[k] = h[k] = 0.0;
-                // the warp streams (column c, column cn, own columns) x all rows through a ring of
-                // chunk slots in its transit-tile area with cp.async, RD chunks ahead: the pass is
-                // no longer a chain of exposed DRAM round trips.  lane <-> row for the copy and
-                // for the arithmetic, so only the thread's own copies have to be waited for.
-                {
-                    constexpr int SLOTW = (2 + KO) * 32;
-                    constexpr int NSLOT = (2 * 32 * TSTR) / SLOTW;
-                    constexpr int RD = (NSLOT - 2 < 8) ? NSLOT - 2 : 8;
-                    double *ring = Tw;
-                    auto issueB = [&](int ch) {
-                        if (ch < nch) {
-                            const int r = m0 + 32 * ch + lane;
-                            double *dst = ring + (ch % NSLOT) * SLOTW + lane;
-                            if (c >= 0) cp_async8_t(dst, Vp + (size_t)c * np + r);
-                            cp_async8_t(dst + 32, P + r + (size_t)cn * lda);
-#pragma unroll
-                            for (int k = 0; k < KO; ++k) {
-                                const int j = wid + WARPS * k;
-                                if (j > cn) cp_async8_t(dst + 64 + 32 * k, P + r + (size_t)j * lda);
-                            }
-                        }
-                        asm volatile("cp.async.commit_group;\n" ::: "memory");
-                    };
-#pragma unroll 1
-                    for (int ch = 0; ch < RD; ++ch) issueB(ch);
-#pragma unroll 1
-                    for (int ch = 0; ch < nch; ++ch) {
-                        issueB(ch + RD);
-                        asm volatile("cp.async.wait_group %0;\n" ::"n"(RD) : "memory");
+            for (int k = 0; k < KO; ++k) g[k] = h[k] = 0.0;
+            // the warp streams (column c, column cn, own columns) x all rows through a ring of
+            // chunk slots in its transit-tile area with cp.async, RD chunks ahead: the pass is
+            // no longer a chain of exposed DRAM round trips.  lane <-> row for the copy and
+            // for the arithmetic, so only the thread's own copies have to be waited for.
+            {
+                constexpr int SLOTW = (2 + KO) * 32;
+                constexpr int NSLOT = (2 * 32 * TSTR) / SLOTW;
+                constexpr int RD = (NSLOT - 2 < 8) ? NSLOT - 2 : 8;
+                double *ring = Tw;
+                auto issueB = [&](int ch) {
+                    if (ch < nch) {
                         const int r = m0 + 32 * ch + lane;
-                        if (r >= rd) {
-                            const double *sl = ring + (ch % NSLOT) * SLOTW + lane;
-                            const double v = (c >= 0) ? sl[0] : 0.0;
-                            const double xc = sl[32];
-                            const double xg = (r > rd + 1) ? xc : 0.0;
+                        double *dst = ring + (ch % NSLOT) * SLOTW + lane;
+                        if (c >= 0) cp_async8_t(dst, Vp + (size_t)c * np + r);
+                        cp_async8_t(dst + 32, P + r + (size_t)cn * lda);
 #pragma unroll
-                            for (int k = 0; k < KO; ++k) {
-                                const int j = wid + WARPS * k;
-                                if (j > cn) {
-                                    double x = sl[64 + 32 * k];
-                                    if (c >= 0) {
-                                        x -= v * wreg[k];
-                                        P[r + (size_t)j * lda] = x;
-                                    }
-                                    g[k] += xg * x;
-                                    if (r == rd + 1) h[k] = x;
+                        for (int k = 0; k < KO; ++k) {
+                            const int j = wid + WARPS * k;
+                            if (j > cn) cp_async8_t(dst + 64 + 32 * k, P + r + (size_t)j * lda);
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                };
+#pragma unroll 1
+                for (int ch = 0; ch < RD; ++ch) issueB(ch);
+#pragma unroll 1
+                for (int ch = 0; ch < nch; ++ch) {
+                    issueB(ch + RD);
+                    asm volatile("cp.async.wait_group %0;\n" ::"n"(RD) : "memory");
+                    const int r = m0 + 32 * ch + lane;
+                    if (r >= rd) {
+                        const double *sl = ring + (ch % NSLOT) * SLOTW + lane;
+                        const double v = (c >= 0) ? sl[0] : 0.0;
+                        const double xc = sl[32];
+                        const double xg = (r > rd + 1) ? xc : 0.0;
+#pragma unroll
+                        for (int k = 0; k < KO; ++k) {
+                            const int j = wid + WARPS * k;
+                            if (j > cn) {
+                                double x = sl[64 + 32 * k];
+                                if (c >= 0) {
+                                    x -= v * wreg[k];
+                                    P[r + (size_t)j * lda] = x;
                                 }
-                            }
-                        }
-                    }
-                    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-                }
-#pragma unroll
-                for (int k = 0; k < KO; ++k) {
-                    g[k] = warp_sum(g[k]);
-                    h[k] = __shfl_sync(ARCB200_FULL_MASK, h[k], cn & 31);   // row m0 + cn: chunk 0, lane cn
-                    wreg[k] = tau_n * (h[k] + scale_n * g[k]);
-                    if (lane == 0) wv[par][wid + WARPS * k] = wreg[k];
-                }
-                tau = tau_n; beta = beta_n; scale = scale_n;
-                __syncthreads();                                     // #2
-            }
-        }
-        __syncthreads();
-        TSP(1)
-
-        // ---------------------------------------------------------------- T factor
-        for (int t = tid; t < 1024; t += NT) { G[t >> 5][t & 31] = 0.0; Ts[t >> 5][t & 31] = 0.0; }
-        __syncthreads();
-        {
-            double acc[4][4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            for (int ch = wid; ch < nch; ch += WARPS) {
-                const int r0 = m0 + 32 * ch;
-                double f[4][8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) f[i][ks] = Vp[(size_t)(8 * i + grp) * np + r0 + 4 * ks + tig];
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dmma_t(acc[i][j][0], acc[i][j][1], f[i][ks], f[j][ks]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) atomicAdd(&G[8 * i + grp][8 * j + 2 * tig + h], acc[i][j][h]);
-        }
-        __syncthreads();
-        if (wid == 0) {
-            // T(0:i, i) = -tau_i T(0:i, 0:i) G(0:i, i); T(i,i) = tau_i   (dlarft forward/columnwise)
-            const int j = lane;
-            for (int i = 0; i < 32; ++i) {
-                const double ti = taus[i];
-                double s = 0.0;
-                if (j < i) {
-                    for (int l = j; l < i; ++l) s += Ts[j][l] * G[l][i];
-                    s *= -ti;
-                } else if (j == i) {
-                    s = ti;
-                }
-                __syncwarp();
-                if (j <= i) Ts[j][i] = s;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        for (int t = tid; t < 1024; t += NT) Tfac[(size_t)p * 1024 + t] = Ts[t >> 5][t & 31];
-
-        TSP(2)
-        // ---------------------------------------------------------------- X = A22 V
-        // Row block i of X = sum_q Asym(i, q) V_q: warp <-> i (groups of WARPS block rows).  The
-        // stored tile (lower triangle; transposed use when q > i) arrives in the warp's transit
-        // tile by cp.async while the previous product runs; V_q is shared through shared memory.
-        const int Jt = p + 1;
-        constexpr int SV = 32 / WARPS;
-        for (int g0 = Jt; g0 < NB; g0 += WARPS) {
-            const int i = g0 + wid;
-            const bool act = i < NB;
-            double acc[4][4][2];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            auto fillV = [&](int buf, int q) {
-#pragma unroll
-                for (int n = 0; n < SV; ++n)
-                    cp_async8_t(&Bs[buf][0][wid + WARPS * n][lane], &Vp[(size_t)(wid + WARPS * n) * np + 32 * q + lane]);
-            };
-            __syncthreads();
-            if (act) issue_tile(max(i, Jt), min(i, Jt), 0);
-            fillV(0, Jt);
-            cp_async_wait_all_t();
-            __syncthreads();
-            for (int q = Jt; q < NB; ++q) {
-                const int buf = (q - Jt) & 1;
-                if (q + 1 < NB) {
-                    if (act) issue_tile(max(i, q + 1), min(i, q + 1), buf ^ 1);
-                    fillV(buf ^ 1, q + 1);
-                }
-                if (act) {
-                    // fragments straight from the transit tile inside the k loop (no register
-                    // array); diagonal tiles are kept fully symmetric, so q == i reads like a
-                    // stored tile
-                    const double *tw = Tw + buf * (32 * TSTR);
-                    if (q <= i) {
-                        const double *pd = tw + tig * TSTR + grp;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            double fa[4];
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
-#pragma unroll
-                            for (int y = 0; y < 4; ++y) {
-                                const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
-#pragma unroll
-                                for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
-                            }
-                        }
-                    } else {
-                        const double *pt = tw + grp * TSTR + tig;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            double fa[4];
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
-#pragma unroll
-                            for (int y = 0; y < 4; ++y) {
-                                const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
-#pragma unroll
-                                for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                                g[k] += xg * x;
+                                if (r == rd + 1) h[k] = x;
                             }
                         }
                     }
                 }
-                cp_async_wait_all_t();
-                __syncthreads();
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             }
-            if (act) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            Wp[(size_t)(8 * y + 2 * tig + h) * np + 32 * i + 8 * x + grp] = acc[x][y][h];
+            for (int k = 0; k < KO; ++k) {
+                g[k] = warp_sum(g[k]);
+                h[k] = __shfl_sync(ARCB200_FULL_MASK, h[k], cn & 31);   // row m0 + cn: chunk 0, lane cn
+                wreg[k] = tau_n * (h[k] + scale_n * g[k]);
+                if (lane == 0) wv[par][wid + WARPS * k] = wreg[k];
             }
+            tau = tau_n; beta = beta_n; scale = scale_n;
+            __syncthreads();                                     // #2
         }
-        __syncthreads();
-        TSP(3)
+    }
+    __syncthreads();
+}
 
-        // ---------------------------------------------------------------- W
-        for (int t = tid; t < 1024; t += NT) G[t >> 5][t & 31] = 0.0;
-        __syncthreads();
-        {
-            // S = V^T X
-            double acc[4][4][2];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            for (int ch = wid; ch < nch; ch += WARPS) {
-                const int r0 = m0 + 32 * ch;
-                double fv[4][8], fx[4][8];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        fv[x][ks] = Vp[(size_t)(8 * x + grp) * np + r0 + 4 * ks + tig];
-                        fx[x][ks] = Wp[(size_t)(8 * x + grp) * np + r0 + 4 * ks + tig];
-                    }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) dmma_t(acc[x][y][0], acc[x][y][1], fv[x][ks], fx[y][ks]);
-            }
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) atomicAdd(&G[8 * x + grp][8 * y + 2 * tig + h], acc[x][y][h]);
+// compact-WY factor T of the panel reflectors (Gram matrix on DMMA), stored to Tfac
+template <int WARPS>
+__device__ __forceinline__ void s1_tfactor(const S1Ctx &c, int p)
+{
+    const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
+    const int np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *__restrict__ tt = c.tt;
+    double *__restrict__ Tfac = c.Tfac;
+    double(*Bs)[2][32][BSTR] = c.Bs;
+    double(*Ts)[33] = c.Ts;
+    double(*G)[33] = c.G;
+    double(*M1)[33] = c.M1;
+    double(*wv)[32] = c.wv;
+    double(*sred)[16] = c.sred;
+    double *taus = c.taus;
+    double *Tw = c.Tw;
+    constexpr int NT = WARPS * 32;
+    constexpr int TSTR = S1_TSTR;
+    const int m0 = 32 * (p + 1), col0 = 32 * p;
+    const int nch = NB - (p + 1);
+    double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
+    const int Jt = p + 1;
+    constexpr int SV = 32 / WARPS;
+    (void)tid; (void)grp; (void)tig; (void)np; (void)Wp; (void)Vp; (void)tt; (void)Tfac; (void)Bs; (void)Ts; (void)G;
+    (void)M1; (void)wv; (void)sred; (void)taus; (void)Tw; (void)NT; (void)m0; (void)col0; (void)nch; (void)P; (void)Jt;
+    (void)SV; (void)lane; (void)wid; (void)lda; (void)NB; (void)A;
+    // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
+    // tile: 16-byte pieces, whole 256-byte column segments per half warp
+    auto issue_tile = [&](int Ib, int Jb, int tb) {
+        // a real loop with running pointers: sixteen hoisted 64-bit addresses would cost 48
+        // registers in the middle of the tensor-core loops
+        const double *src = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+        double *dst = Tw + tb * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+        const size_t sstep = 2 * (size_t)lda;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            cp_async16_t(dst, src);
+            src += sstep;
+            dst += 2 * TSTR;
         }
-        __syncthreads();
-        // M1 = S T
-        for (int t = tid; t < 1024; t += NT) {
-            const int row = t >> 5, col = t & 31;
-            double s = 0.0;
-            for (int l = 0; l <= col; ++l) s += G[row][l] * Ts[l][col];
-            M1[row][col] = s;
-        }
-        __syncthreads();
-        // M2 = T^T M1 -> G
-        for (int t = tid; t < 1024; t += NT) {
-            const int row = t >> 5, col = t & 31;
-            double s = 0.0;
-            for (int l = 0; l <= row; ++l) s += Ts[l][row] * M1[l][col];
-            G[row][col] = s;
-        }
-        __syncthreads();
-        // operand tiles [n][k]: T and -M2/2
-        for (int t = tid; t < 1024; t += NT) {
-            const int n = t >> 5, k = t & 31;
-            Bs[0][0][n][k] = Ts[k][n];
-            Bs[0][1][n][k] = -0.5 * G[k][n];
-        }
-        __syncthreads();
+    };
+    (void)issue_tile;
+    // ---------------------------------------------------------------- T factor
+    for (int t = tid; t < 1024; t += NT) { G[t >> 5][t & 31] = 0.0; Ts[t >> 5][t & 31] = 0.0; }
+    __syncthreads();
+    {
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         for (int ch = wid; ch < nch; ch += WARPS) {
             const int r0 = m0 + 32 * ch;
-            double fx[4][8], fv[4][8];
+            double f[4][8];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    fx[x][ks] = Wp[(size_t)(4 * ks + tig) * np + r0 + 8 * x + grp];
-                    fv[x][ks] = Vp[(size_t)(4 * ks + tig) * np + r0 + 8 * x + grp];
-                }
-            double acc[4][4][2];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+                for (int ks = 0; ks < 8; ++ks) f[i][ks] = Vp[(size_t)(8 * i + grp) * np + r0 + 4 * ks + tig];
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const double bt = Bs[0][0][8 * y + grp][4 * ks + tig];
-                    const double bm = Bs[0][1][8 * y + grp][4 * ks + tig];
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        dmma_t(acc[x][y][0], acc[x][y][1], fx[x][ks], bt);
-                        dmma_t(acc[x][y][0], acc[x][y][1], fv[x][ks], bm);
+                    for (int j = 0; j < 4; ++j) dmma_t(acc[i][j][0], acc[i][j][1], f[i][ks], f[j][ks]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) atomicAdd(&G[8 * i + grp][8 * j + 2 * tig + h], acc[i][j][h]);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        // T(0:i, i) = -tau_i T(0:i, 0:i) G(0:i, i); T(i,i) = tau_i   (dlarft forward/columnwise)
+        const int j = lane;
+        for (int i = 0; i < 32; ++i) {
+            const double ti = taus[i];
+            double s = 0.0;
+            if (j < i) {
+                for (int l = j; l < i; ++l) s += Ts[j][l] * G[l][i];
+                s *= -ti;
+            } else if (j == i) {
+                s = ti;
+            }
+            __syncwarp();
+            if (j <= i) Ts[j][i] = s;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < 1024; t += NT) Tfac[(size_t)p * 1024 + t] = Ts[t >> 5][t & 31];
+}
+
+// X = A22 V, all WARPS warps in lockstep over q (one block barrier per step)
+template <int WARPS>
+__device__ __forceinline__ void s1_symm_lockstep(const S1Ctx &c, int p)
+{
+    const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
+    const int np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *__restrict__ tt = c.tt;
+    double *__restrict__ Tfac = c.Tfac;
+    double(*Bs)[2][32][BSTR] = c.Bs;
+    double(*Ts)[33] = c.Ts;
+    double(*G)[33] = c.G;
+    double(*M1)[33] = c.M1;
+    double(*wv)[32] = c.wv;
+    double(*sred)[16] = c.sred;
+    double *taus = c.taus;
+    double *Tw = c.Tw;
+    constexpr int NT = WARPS * 32;
+    constexpr int TSTR = S1_TSTR;
+    const int m0 = 32 * (p + 1), col0 = 32 * p;
+    const int nch = NB - (p + 1);
+    double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
+    const int Jt = p + 1;
+    constexpr int SV = 32 / WARPS;
+    (void)tid; (void)grp; (void)tig; (void)np; (void)Wp; (void)Vp; (void)tt; (void)Tfac; (void)Bs; (void)Ts; (void)G;
+    (void)M1; (void)wv; (void)sred; (void)taus; (void)Tw; (void)NT; (void)m0; (void)col0; (void)nch; (void)P; (void)Jt;
+    (void)SV; (void)lane; (void)wid; (void)lda; (void)NB; (void)A;
+    // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
+    // tile: 16-byte pieces, whole 256-byte column segments per half warp
+    auto issue_tile = [&](int Ib, int Jb, int tb) {
+        // a real loop with running pointers: sixteen hoisted 64-bit addresses would cost 48
+        // registers in the middle of the tensor-core loops
+        const double *src = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+        double *dst = Tw + tb * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+        const size_t sstep = 2 * (size_t)lda;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            cp_async16_t(dst, src);
+            src += sstep;
+            dst += 2 * TSTR;
+        }
+    };
+    (void)issue_tile;
+    // ---------------------------------------------------------------- X = A22 V
+    // Row block i of X = sum_q Asym(i, q) V_q: warp <-> i (groups of WARPS block rows).  The
+    // stored tile (lower triangle; transposed use when q > i) arrives in the warp's transit
+    // tile by cp.async while the previous product runs; V_q is shared through shared memory.
+            for (int g0 = Jt; g0 < NB; g0 += WARPS) {
+        const int i = g0 + wid;
+        const bool act = i < NB;
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        auto fillV = [&](int buf, int q) {
+#pragma unroll
+            for (int n = 0; n < SV; ++n)
+                cp_async8_t(&Bs[buf][0][wid + WARPS * n][lane], &Vp[(size_t)(wid + WARPS * n) * np + 32 * q + lane]);
+        };
+        __syncthreads();
+        if (act) issue_tile(max(i, Jt), min(i, Jt), 0);
+        fillV(0, Jt);
+        cp_async_wait_all_t();
+        __syncthreads();
+        for (int q = Jt; q < NB; ++q) {
+            const int buf = (q - Jt) & 1;
+            if (q + 1 < NB) {
+                if (act) issue_tile(max(i, q + 1), min(i, q + 1), buf ^ 1);
+                fillV(buf ^ 1, q + 1);
+            }
+            if (act) {
+                // fragments straight from the transit tile inside the k loop (no register
+                // array); diagonal tiles are kept fully symmetric, so q == i reads like a
+                // stored tile
+                const double *tw = Tw + buf * (32 * TSTR);
+                if (q <= i) {
+                    const double *pd = tw + tig * TSTR + grp;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double fa[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                        }
+                    }
+                } else {
+                    const double *pt = tw + grp * TSTR + tig;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double fa[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double b = Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                        }
                     }
                 }
-            __syncwarp();
+            }
+            cp_async_wait_all_t();
+            __syncthreads();
+        }
+        if (act) {
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        Wp[(size_t)(8 * y + 2 * tig + h) * np + r0 + 8 * x + grp] = acc[x][y][h];
+                        Wp[(size_t)(8 * y + 2 * tig + h) * np + 32 * i + 8 * x + grp] = acc[x][y][h];
         }
-        __syncthreads();
-        TSP(4)
+    }
+    __syncthreads();
+}
 
-        // ---------------------------------------------------------------- A22 -= V W^T + W V^T
-        // warp <-> block row I (groups of WARPS): the A-operand fragments -V_I, -W_I stay in
-        // registers for the whole sweep over J <= I; W_J, V_J are shared through shared memory;
-        // the next C tile arrives in the transit tile by cp.async during the 256 DMMAs.
-        // Fragment row mapping here: DMMA row (x, grp) <-> tile row 4 grp + x, so that a lane's
-        // four rows are contiguous (128-bit shared loads and global stores).
-        for (int g0 = Jt; g0 < NB; g0 += WARPS) {
-            const int I = g0 + wid;
-            const bool act = I < NB;
-            const int Jmax = min(g0 + WARPS - 1, NB - 1);
-            // -W_I in registers; -V_I in the warp's second transit tile ([k][row], pitch TSTR)
-            double fw[4][8];
-            if (act) {
+// W = X T - 1/2 V (T^T (V^T X) T)
+template <int WARPS>
+__device__ __forceinline__ void s1_wphase(const S1Ctx &c, int p)
+{
+    const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
+    const int np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *__restrict__ tt = c.tt;
+    double *__restrict__ Tfac = c.Tfac;
+    double(*Bs)[2][32][BSTR] = c.Bs;
+    double(*Ts)[33] = c.Ts;
+    double(*G)[33] = c.G;
+    double(*M1)[33] = c.M1;
+    double(*wv)[32] = c.wv;
+    double(*sred)[16] = c.sred;
+    double *taus = c.taus;
+    double *Tw = c.Tw;
+    constexpr int NT = WARPS * 32;
+    constexpr int TSTR = S1_TSTR;
+    const int m0 = 32 * (p + 1), col0 = 32 * p;
+    const int nch = NB - (p + 1);
+    double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
+    const int Jt = p + 1;
+    constexpr int SV = 32 / WARPS;
+    (void)tid; (void)grp; (void)tig; (void)np; (void)Wp; (void)Vp; (void)tt; (void)Tfac; (void)Bs; (void)Ts; (void)G;
+    (void)M1; (void)wv; (void)sred; (void)taus; (void)Tw; (void)NT; (void)m0; (void)col0; (void)nch; (void)P; (void)Jt;
+    (void)SV; (void)lane; (void)wid; (void)lda; (void)NB; (void)A;
+    // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
+    // tile: 16-byte pieces, whole 256-byte column segments per half warp
+    auto issue_tile = [&](int Ib, int Jb, int tb) {
+        // a real loop with running pointers: sixteen hoisted 64-bit addresses would cost 48
+        // registers in the middle of the tensor-core loops
+        const double *src = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+        double *dst = Tw + tb * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+        const size_t sstep = 2 * (size_t)lda;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            cp_async16_t(dst, src);
+            src += sstep;
+            dst += 2 * TSTR;
+        }
+    };
+    (void)issue_tile;
+    // ---------------------------------------------------------------- W
+    for (int t = tid; t < 1024; t += NT) G[t >> 5][t & 31] = 0.0;
+    __syncthreads();
+    {
+        // S = V^T X
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        for (int ch = wid; ch < nch; ch += WARPS) {
+            const int r0 = m0 + 32 * ch;
+            double fv[4][8], fx[4][8];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
-                    const double2 w0 = pw2[0], w1 = pw2[1];
-                    fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
+                    fv[x][ks] = Vp[(size_t)(8 * x + grp) * np + r0 + 4 * ks + tig];
+                    fx[x][ks] = Wp[(size_t)(8 * x + grp) * np + r0 + 4 * ks + tig];
+                }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) dmma_t(acc[x][y][0], acc[x][y][1], fv[x][ks], fx[y][ks]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) atomicAdd(&G[8 * x + grp][8 * y + 2 * tig + h], acc[x][y][h]);
+    }
+    __syncthreads();
+    // M1 = S T
+    for (int t = tid; t < 1024; t += NT) {
+        const int row = t >> 5, col = t & 31;
+        double s = 0.0;
+        for (int l = 0; l <= col; ++l) s += G[row][l] * Ts[l][col];
+        M1[row][col] = s;
+    }
+    __syncthreads();
+    // M2 = T^T M1 -> G
+    for (int t = tid; t < 1024; t += NT) {
+        const int row = t >> 5, col = t & 31;
+        double s = 0.0;
+        for (int l = 0; l <= row; ++l) s += Ts[l][row] * M1[l][col];
+        G[row][col] = s;
+    }
+    __syncthreads();
+    // operand tiles [n][k]: T and -M2/2
+    for (int t = tid; t < 1024; t += NT) {
+        const int n = t >> 5, k = t & 31;
+        Bs[0][0][n][k] = Ts[k][n];
+        Bs[0][1][n][k] = -0.5 * G[k][n];
+    }
+    __syncthreads();
+    for (int ch = wid; ch < nch; ch += WARPS) {
+        const int r0 = m0 + 32 * ch;
+        double fx[4][8], fv[4][8];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                fx[x][ks] = Wp[(size_t)(4 * ks + tig) * np + r0 + 8 * x + grp];
+                fv[x][ks] = Vp[(size_t)(4 * ks + tig) * np + r0 + 8 * x + grp];
+            }
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const double bt = Bs[0][0][8 * y + grp][4 * ks + tig];
+                const double bm = Bs[0][1][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    dmma_t(acc[x][y][0], acc[x][y][1], fx[x][ks], bt);
+                    dmma_t(acc[x][y][0], acc[x][y][1], fv[x][ks], bm);
                 }
             }
-            double *Tv = Tw + 32 * TSTR;
-            auto fillWV = [&](int buf, int J) {
+        __syncwarp();
 #pragma unroll
-                for (int n = 0; n < SV; ++n) {
-                    cp_async8_t(&Bs[buf][0][lane][wid + WARPS * n], &Wp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
-                    cp_async8_t(&Bs[buf][1][lane][wid + WARPS * n], &Vp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
-                }
-            };
-            __syncthreads();
-            if (act) {
-                issue_tile(I, Jt, 0);
-                // V_I: panel columns k = 0..31, rows 32 I .. 32 I + 31
-                const double *src = Vp + (size_t)(lane >> 4) * np + 32 * I + (lane & 15) * 2;
-                double *dst = Tv + (lane >> 4) * TSTR + (lane & 15) * 2;
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    Wp[(size_t)(8 * y + 2 * tig + h) * np + r0 + 8 * x + grp] = acc[x][y][h];
+    }
+    __syncthreads();
+}
+
+// A22 -= V W^T + W V^T, all WARPS warps in lockstep over J (one block barrier per step)
+template <int WARPS>
+__device__ __forceinline__ void s1_syr2k_lockstep(const S1Ctx &c, int p)
+{
+    const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
+    const int np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *__restrict__ tt = c.tt;
+    double *__restrict__ Tfac = c.Tfac;
+    double(*Bs)[2][32][BSTR] = c.Bs;
+    double(*Ts)[33] = c.Ts;
+    double(*G)[33] = c.G;
+    double(*M1)[33] = c.M1;
+    double(*wv)[32] = c.wv;
+    double(*sred)[16] = c.sred;
+    double *taus = c.taus;
+    double *Tw = c.Tw;
+    constexpr int NT = WARPS * 32;
+    constexpr int TSTR = S1_TSTR;
+    const int m0 = 32 * (p + 1), col0 = 32 * p;
+    const int nch = NB - (p + 1);
+    double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
+    const int Jt = p + 1;
+    constexpr int SV = 32 / WARPS;
+    (void)tid; (void)grp; (void)tig; (void)np; (void)Wp; (void)Vp; (void)tt; (void)Tfac; (void)Bs; (void)Ts; (void)G;
+    (void)M1; (void)wv; (void)sred; (void)taus; (void)Tw; (void)NT; (void)m0; (void)col0; (void)nch; (void)P; (void)Jt;
+    (void)SV; (void)lane; (void)wid; (void)lda; (void)NB; (void)A;
+    // asynchronous copy of the stored 32x32 tile (Ib, Jb), Ib >= Jb, into this warp's transit
+    // tile: 16-byte pieces, whole 256-byte column segments per half warp
+    auto issue_tile = [&](int Ib, int Jb, int tb) {
+        // a real loop with running pointers: sixteen hoisted 64-bit addresses would cost 48
+        // registers in the middle of the tensor-core loops
+        const double *src = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+        double *dst = Tw + tb * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+        const size_t sstep = 2 * (size_t)lda;
 #pragma unroll 1
-                for (int k = 0; k < 16; ++k) {
-                    cp_async16_t(dst, src);
-                    src += 2 * (size_t)np;
-                    dst += 2 * TSTR;
-                }
-            }
-            fillWV(0, Jt);
-            cp_async_wait_all_t();
-            __syncwarp();
-            if (act) {
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) Tv[lane * TSTR + r] = -Tv[lane * TSTR + r];
-            }
-            __syncthreads();
-            const double *tv = Tv + tig * TSTR + 4 * grp;
-            const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
-            for (int J = Jt; J <= Jmax; ++J) {
-                const int buf = (J - Jt) & 1;
-                const bool work = act && J <= I;
-                double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
-                if (work) {
+        for (int k = 0; k < 16; ++k) {
+            cp_async16_t(dst, src);
+            src += sstep;
+            dst += 2 * TSTR;
+        }
+    };
+    (void)issue_tile;
+    // ---------------------------------------------------------------- A22 -= V W^T + W V^T
+    // warp <-> block row I (groups of WARPS): the A-operand fragments -V_I, -W_I stay in
+    // registers for the whole sweep over J <= I; W_J, V_J are shared through shared memory;
+    // the next C tile arrives in the transit tile by cp.async during the 256 DMMAs.
+    // Fragment row mapping here: DMMA row (x, grp) <-> tile row 4 grp + x, so that a lane's
+    // four rows are contiguous (128-bit shared loads and global stores).
+    for (int g0 = Jt; g0 < NB; g0 += WARPS) {
+        const int I = g0 + wid;
+        const bool act = I < NB;
+        const int Jmax = min(g0 + WARPS - 1, NB - 1);
+        // -W_I in registers; -V_I in the warp's second transit tile ([k][row], pitch TSTR)
+        double fw[4][8];
+        if (act) {
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
-                        const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
-                        const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
-                        c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
-                        c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
-                    }
-                }
-                __syncwarp();
-                if (J + 1 <= Jmax) {
-                    if (act && J + 1 <= I) issue_tile(I, J + 1, 0);
-                    fillWV(buf ^ 1, J + 1);
-                }
-                if (work) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
-                        const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
-                        const double fv[4] = {va.x, va.y, vb.x, vb.y};
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
-                            const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) {
-                                dmma_t(c0[x][y], c1[x][y], fv[x], bw);
-                                dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
-                            }
-                        }
-                    }
-                    double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
-                        double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
-                        o0[0] = make_double2(c0[0][y], c0[1][y]);
-                        o0[1] = make_double2(c0[2][y], c0[3][y]);
-                        o1[0] = make_double2(c1[0][y], c1[1][y]);
-                        o1[1] = make_double2(c1[2][y], c1[3][y]);
-                    }
-                }
-                cp_async_wait_all_t();
-                __syncthreads();
+            for (int ks = 0; ks < 8; ++ks) {
+                const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                const double2 w0 = pw2[0], w1 = pw2[1];
+                fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
             }
         }
-        TSP(5)
-    }  // panels
-#ifdef TS_PROFILE
-    if (mat == 0 && tid == 0)
-        printf("sy2sb prof (10 kcycles): qr %lld tfac %lld symm %lld w %lld syr2k %lld\n", tsp_t[1] / 10000,
-               tsp_t[2] / 10000, tsp_t[3] / 10000, tsp_t[4] / 10000, tsp_t[5] / 10000);
-#endif
+        double *Tv = Tw + 32 * TSTR;
+        auto fillWV = [&](int buf, int J) {
+#pragma unroll
+            for (int n = 0; n < SV; ++n) {
+                cp_async8_t(&Bs[buf][0][lane][wid + WARPS * n], &Wp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
+                cp_async8_t(&Bs[buf][1][lane][wid + WARPS * n], &Vp[(size_t)(wid + WARPS * n) * np + 32 * J + lane]);
+            }
+        };
+        __syncthreads();
+        if (act) {
+            issue_tile(I, Jt, 0);
+            // V_I: panel columns k = 0..31, rows 32 I .. 32 I + 31
+            const double *src = Vp + (size_t)(lane >> 4) * np + 32 * I + (lane & 15) * 2;
+            double *dst = Tv + (lane >> 4) * TSTR + (lane & 15) * 2;
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) {
+                cp_async16_t(dst, src);
+                src += 2 * (size_t)np;
+                dst += 2 * TSTR;
+            }
+        }
+        fillWV(0, Jt);
+        cp_async_wait_all_t();
+        __syncwarp();
+        if (act) {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) Tv[lane * TSTR + r] = -Tv[lane * TSTR + r];
+        }
+        __syncthreads();
+        const double *tv = Tv + tig * TSTR + 4 * grp;
+        const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
+        for (int J = Jt; J <= Jmax; ++J) {
+            const int buf = (J - Jt) & 1;
+            const bool work = act && J <= I;
+            double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
+            if (work) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
+                    const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
+                    const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                    c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
+                    c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
+                }
+            }
+            __syncwarp();
+            if (J + 1 <= Jmax) {
+                if (act && J + 1 <= I) issue_tile(I, J + 1, 0);
+                fillWV(buf ^ 1, J + 1);
+            }
+            if (work) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
+                    const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
+                    const double fv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
+                        const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
+                        }
+                    }
+                }
+                double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
+                    double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
+                    o0[0] = make_double2(c0[0][y], c0[1][y]);
+                    o0[1] = make_double2(c0[2][y], c0[3][y]);
+                    o1[0] = make_double2(c1[0][y], c1[1][y]);
+                    o1[1] = make_double2(c1[2][y], c1[3][y]);
+                }
+            }
+            cp_async_wait_all_t();
+            __syncthreads();
+        }
+    }
+}
 
-    // ------------------------------------------------------------ compact lower band (N x N part)
+// ------------------------------------------------------------------------------------------
+// decoupled warpgroups + TMA-unit bulk copies (the default band-reduction kernel)
+// ------------------------------------------------------------------------------------------
+// ncu of the lockstep kernel (profiles/r02_sy2sb_lockstep_*): inside the k loops the FP64 tensor
+// pipe is saturated (one DMMA per 16 cycles and scheduler, the two warps of a scheduler alternate
+// in groups of four), but every step of the symmetric product / rank-2k update ends in a block
+// barrier, so the per-step prologue and epilogue (operand waits, fragment loads of the C tile,
+// 128-bit stores, next-tile issue) of all eight warps coincide and the pipe idles: 69 % / 59 % of
+// the DMMA rate inside those phases.  Here the eight warps form two warpgroups of four that take
+// row groups of four block rows from a dispenser and run them independently (named barriers,
+// private operand tiles): warps w and w + 4 share a scheduler, so one warpgroup's prologue and
+// epilogue overlap the other's DMMA loop, and the triangular tail of a row group is four steps
+// instead of eight.  All tile movement of these phases goes through the TMA unit: one
+// cp.async.bulk per lane moves a 256-byte tile column (SASS UBLKCP), completion is tracked by
+// mbarriers (SYNCS) -- no per-thread cp.async address loops, no cp.async.wait_group.
+static __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one bulk copy (TMA unit): `bytes` contiguous bytes global -> shared, completion counted on `bar`
+static __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+static __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+static __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory"); }
+
+struct S1Wg {                      // warpgroup-private state of the decoupled phases
+    double(*Bs)[2][32][BSTR];      // this warpgroup's operand tiles [buf][op][row][col]
+    unsigned long long *tbar;      // this warp's two tile barriers
+    unsigned long long *bbar;      // this warpgroup's two operand barriers
+    int *next;                     // row-group dispenser of the CTA
+    volatile int *cur;             // row group taken by this warpgroup
+    int wg, wl;                    // warpgroup, warp inside it
+};
+
+// X = A22 V.  Warp <-> block row i of a group of four; the stored tile (i, q) (transposed use when
+// q > i) and the shared operand V_q arrive by bulk copies one step ahead.
+static __device__ __forceinline__ void s1_symm_wg(const S1Ctx &c, const S1Wg &g, int p, unsigned &tph, unsigned &bph)
+{
+    constexpr int TSTR = S1_TSTR;
+    const int lane = c.lane, grp = c.grp, tig = c.tig, np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *Tw = c.Tw;
+    const int Jt = p + 1, nch = NB - (p + 1);
+    const int ng = (nch + 3) >> 2;
+    if (c.tid == 0) *g.next = 0;
+    __syncthreads();
+    fence_async_proxy();           // generic-proxy writes of the earlier phases before the bulk copies
+    auto issue_tile = [&](int Ib, int Jb, int tb) {      // lane <-> tile column (256 contiguous bytes)
+        if (lane == 0) mbar_expect_tx(&g.tbar[tb], 32 * 32 * 8);
+        __syncwarp();
+        bulk_g2s(Tw + tb * (32 * TSTR) + lane * TSTR, A + (size_t)(32 * Jb + lane) * lda + 32 * Ib, 256, &g.tbar[tb]);
+    };
+    auto fillV = [&](int buf, int q) {                   // V_q as [n][k]: row n = panel column n
+        if (g.wl == 0) {
+            if (lane == 0) mbar_expect_tx(&g.bbar[buf], 32 * 32 * 8);
+            __syncwarp();
+            bulk_g2s(&g.Bs[buf][0][lane][0], Vp + (size_t)lane * np + 32 * q, 256, &g.bbar[buf]);
+        }
+    };
+    for (;;) {
+        if (g.wl == 0 && lane == 0) *g.cur = atomicAdd(g.next, 1);
+        wg_bar(g.wg);
+        const int t = *g.cur;
+        if (t >= ng) break;
+        const int i = Jt + 4 * t + g.wl;
+        const bool act = i < NB;
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        if (act) issue_tile(max(i, Jt), min(i, Jt), 0);
+        fillV(0, Jt);
+        for (int q = Jt; q < NB; ++q) {
+            const int buf = (q - Jt) & 1;
+            if (q + 1 < NB) {
+                if (act) issue_tile(max(i, q + 1), min(i, q + 1), buf ^ 1);
+                fillV(buf ^ 1, q + 1);
+            }
+            mbar_wait(&g.bbar[buf], (bph >> buf) & 1u);
+            bph ^= 1u << buf;
+            if (act) {
+                mbar_wait(&g.tbar[buf], (tph >> buf) & 1u);
+                tph ^= 1u << buf;
+                // fragments straight from the transit tile inside the k loop; diagonal tiles are
+                // kept fully symmetric, so q == i reads like a stored tile
+                const double *tw = Tw + buf * (32 * TSTR);
+                if (q <= i) {
+                    const double *pd = tw + tig * TSTR + grp;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double fa[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double b = g.Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                        }
+                    }
+                } else {
+                    const double *pt = tw + grp * TSTR + tig;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double fa[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double b = g.Bs[buf][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                        }
+                    }
+                }
+            }
+            wg_bar(g.wg);          // the four warps are done with Bs[buf]
+        }
+        if (act) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        Wp[(size_t)(8 * y + 2 * tig + h) * np + 32 * i + 8 * x + grp] = acc[x][y][h];
+        }
+    }
+    __syncthreads();
+}
+
+// A22 -= V W^T + W V^T.  Warp <-> block row I of a group of four (largest groups first): -W_I
+// stays in registers, -V_I in the warp's second transit tile, W_J / V_J ([k][n]: row k = panel
+// column) are shared by the warpgroup, the C tile arrives one step ahead.  DMMA row (x, grp) <->
+// tile row 4 grp + x, so a lane's four rows are contiguous (128-bit shared loads, global stores).
+static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g, int p, unsigned &tph, unsigned &bph)
+{
+    constexpr int TSTR = S1_TSTR;
+    const int lane = c.lane, grp = c.grp, tig = c.tig, np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *Tw = c.Tw;
+    double *Tv = Tw + 32 * TSTR;
+    const int Jt = p + 1, nch = NB - (p + 1);
+    const int ng = (nch + 3) >> 2;
+    if (c.tid == 0) *g.next = 0;
+    __syncthreads();
+    fence_async_proxy();
+    auto issue_tile = [&](int Ib, int Jb) {
+        if (lane == 0) mbar_expect_tx(&g.tbar[0], 32 * 32 * 8);
+        __syncwarp();
+        bulk_g2s(Tw + lane * TSTR, A + (size_t)(32 * Jb + lane) * lda + 32 * Ib, 256, &g.tbar[0]);
+    };
+    auto fillWV = [&](int buf, int J) {
+        if (g.wl == 0) {
+            if (lane == 0) mbar_expect_tx(&g.bbar[buf], 2 * 32 * 32 * 8);
+            __syncwarp();
+            bulk_g2s(&g.Bs[buf][0][lane][0], Wp + (size_t)lane * np + 32 * J, 256, &g.bbar[buf]);
+            bulk_g2s(&g.Bs[buf][1][lane][0], Vp + (size_t)lane * np + 32 * J, 256, &g.bbar[buf]);
+        }
+    };
+    for (;;) {
+        if (g.wl == 0 && lane == 0) *g.cur = atomicAdd(g.next, 1);
+        wg_bar(g.wg);
+        const int tt_ = *g.cur;
+        if (tt_ >= ng) break;
+        const int g0 = Jt + 4 * (ng - 1 - tt_);
+        const int I = g0 + g.wl;
+        const bool act = I < NB;
+        const int Jmax = min(g0 + 3, NB - 1);
+        if (act) {
+            issue_tile(I, Jt);
+            // V_I: panel columns k = 0..31 (lane <-> k), rows 32 I .. 32 I + 31
+            if (lane == 0) mbar_expect_tx(&g.tbar[1], 32 * 32 * 8);
+            __syncwarp();
+            bulk_g2s(Tv + lane * TSTR, Vp + (size_t)lane * np + 32 * I, 256, &g.tbar[1]);
+        }
+        fillWV(0, Jt);
+        double fw[4][8];
+        if (act) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                const double2 w0 = pw2[0], w1 = pw2[1];
+                fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
+            }
+            mbar_wait(&g.tbar[1], (tph >> 1) & 1u);
+            tph ^= 2u;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) Tv[lane * TSTR + r] = -Tv[lane * TSTR + r];
+            __syncwarp();
+            fence_async_proxy();   // these generic writes precede the next group's bulk copy into Tv
+        }
+        const double *tv = Tv + tig * TSTR + 4 * grp;
+        const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
+        for (int J = Jt; J <= Jmax; ++J) {
+            const int buf = (J - Jt) & 1;
+            const bool work = act && J <= I;
+            mbar_wait(&g.bbar[buf], (bph >> buf) & 1u);
+            bph ^= 1u << buf;
+            double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
+            if (work) {
+                mbar_wait(&g.tbar[0], tph & 1u);
+                tph ^= 1u;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
+                    const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
+                    const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                    c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
+                    c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
+                }
+                // the tile buffer is refilled below: its loads have to have landed
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    asm volatile("" ::"d"(c0[0][y]), "d"(c0[1][y]), "d"(c0[2][y]), "d"(c0[3][y]), "d"(c1[0][y]), "d"(c1[1][y]),
+                                 "d"(c1[2][y]), "d"(c1[3][y]));
+            }
+            __syncwarp();
+            if (J + 1 <= Jmax) {
+                if (act && J + 1 <= I) issue_tile(I, J + 1);
+                fillWV(buf ^ 1, J + 1);
+            }
+            if (work) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
+                    const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
+                    const double fv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double bw = g.Bs[buf][0][4 * ks + tig][8 * y + grp];
+                        const double bv = g.Bs[buf][1][4 * ks + tig][8 * y + grp];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
+                        }
+                    }
+                }
+                double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
+                    double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
+                    o0[0] = make_double2(c0[0][y], c0[1][y]);
+                    o0[1] = make_double2(c0[2][y], c0[3][y]);
+                    o1[0] = make_double2(c1[0][y], c1[1][y]);
+                    o1[1] = make_double2(c1[2][y], c1[3][y]);
+                }
+            }
+            wg_bar(g.wg);
+        }
+    }
+    __syncthreads();
+}
+
+static __device__ __forceinline__ void s1_band_copy(const TsArgs &a, double *slot, double *A, int lda, int tid, int NT)
+{
+    const int np = a.Npad;
     __syncthreads();
     {
         double *__restrict__ Bd = slot + a.oBand;
@@ -585,6 +1052,120 @@ __global__ void __launch_bounds__(WARPS * 32, 8 / WARPS) sy2sb_kernel(TsArgs a)
         }
     }
 }
+
+// WARPS = 8: one CTA per SM; WARPS = 4: one 4-warp CTA per matrix (kept for A/B runs).  All warps in
+// lockstep (one block barrier per tile step), tiles by per-thread cp.async.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_kernel(TsArgs a)
+{
+    constexpr int TSTR = S1_TSTR;
+    constexpr int UNI = 2 * WARPS * 32 * TSTR + 4608;   // 2 transit tiles per warp + operand tiles (doubles)
+    const int mat = blockIdx.x;
+    double *slot = a.base + (size_t)mat * a.slot;
+    extern __shared__ double sm[];
+    S1Ctx c;
+    c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
+    c.np = a.Npad; c.lda = a.Npad; c.NB = a.NB;
+    c.A = slot + a.oA; c.Wp = slot + a.oWp; c.Vp = slot + a.oVp; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
+    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + 2 * WARPS * 32 * TSTR);
+    c.Ts = reinterpret_cast<double(*)[33]>(sm + UNI);
+    c.G = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
+    c.M1 = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
+    c.wv = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056);            // [par][j]
+    c.sred = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 64);     // [par][warp], [par][15] = alpha
+    c.taus = sm + UNI + 3 * 1056 + 96;                                      // [32]
+    c.Tw = sm + c.wid * (2 * 32 * TSTR);
+    TSP_DECL
+    for (int p = 0; p < a.NB - 1; ++p) {
+        TSP(0)
+        s1_panel_qr<WARPS>(c, p);
+        TSP(1)
+        s1_tfactor<WARPS>(c, p);
+        TSP(2)
+        s1_symm_lockstep<WARPS>(c, p);
+        TSP(3)
+        s1_wphase<WARPS>(c, p);
+        TSP(4)
+        s1_syr2k_lockstep<WARPS>(c, p);
+        TSP(5)
+    }
+#ifdef TS_PROFILE
+    if (mat == 0 && c.tid == 0)
+        printf("sy2sb prof (10 kcycles): qr %lld tfac %lld symm %lld w %lld syr2k %lld\n", tsp_t[1] / 10000,
+               tsp_t[2] / 10000, tsp_t[3] / 10000, tsp_t[4] / 10000, tsp_t[5] / 10000);
+#endif
+    __syncthreads();
+    s1_band_copy(a, slot, c.A, c.lda, c.tid, WARPS * 32);
+}
+
+// Default: two decoupled warpgroups, TMA-unit bulk copies + mbarriers (see above).
+constexpr int S1WG_SMEM_DOUBLES = 2 * 8 * 32 * S1_TSTR + 2 * 4608 + 128;
+constexpr size_t S1WG_SMEM_BYTES = (size_t)S1WG_SMEM_DOUBLES * sizeof(double) + 256;
+__global__ void __launch_bounds__(256, 1) sy2sb_wg_kernel(TsArgs a)
+{
+    constexpr int WARPS = 8;
+    constexpr int TSTR = S1_TSTR;
+    constexpr int TILES = 2 * WARPS * 32 * TSTR;
+    const int mat = blockIdx.x;
+    double *slot = a.base + (size_t)mat * a.slot;
+    extern __shared__ double sm[];
+    S1Ctx c;
+    c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
+    c.np = a.Npad; c.lda = a.Npad; c.NB = a.NB;
+    c.A = slot + a.oA; c.Wp = slot + a.oWp; c.Vp = slot + a.oVp; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
+    // [transit tiles][operand tiles of warpgroup 0][operand tiles of warpgroup 1][small arrays][barriers]
+    // T, G, M1 of the T-factor / W phases live in warpgroup 1's operand tiles (idle in those phases;
+    // T is reloaded from global memory after the symmetric product has used them)
+    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+    double *bsB = sm + TILES + 4608;
+    c.Ts = reinterpret_cast<double(*)[33]>(bsB);
+    c.G = reinterpret_cast<double(*)[33]>(bsB + 1056);
+    c.M1 = reinterpret_cast<double(*)[33]>(bsB + 2 * 1056);
+    double *small = sm + TILES + 2 * 4608;
+    c.wv = reinterpret_cast<double(*)[32]>(small);
+    c.sred = reinterpret_cast<double(*)[16]>(small + 64);
+    c.taus = small + 96;
+    c.Tw = sm + c.wid * (2 * 32 * TSTR);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(small + 128);   // 16 tile + 4 operand barriers
+    int *ctl = reinterpret_cast<int *>(bars + 20);                                     // next, cur[2]
+    S1Wg g;
+    g.wg = c.wid >> 2; g.wl = c.wid & 3;
+    g.Bs = g.wg ? reinterpret_cast<double(*)[2][32][BSTR]>(bsB) : c.Bs;
+    g.tbar = bars + 2 * c.wid;
+    g.bbar = bars + 16 + 2 * g.wg;
+    g.next = ctl;
+    g.cur = ctl + 1 + g.wg;
+    if (c.tid == 0) {
+        for (int i = 0; i < 20; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    fence_async_proxy();
+    __syncthreads();
+    unsigned tph = 0, bph = 0;     // phase parities of this warp's tile / this warpgroup's operand barriers
+    TSP_DECL
+    for (int p = 0; p < a.NB - 1; ++p) {
+        TSP(0)
+        s1_panel_qr<WARPS>(c, p);
+        TSP(1)
+        s1_tfactor<WARPS>(c, p);
+        TSP(2)
+        s1_symm_wg(c, g, p, tph, bph);
+        TSP(3)
+        for (int t = c.tid; t < 1024; t += WARPS * 32) c.Ts[t >> 5][t & 31] = c.Tfac[(size_t)p * 1024 + t];
+        s1_wphase<WARPS>(c, p);
+        TSP(4)
+        s1_syr2k_wg(c, g, p, tph, bph);
+        TSP(5)
+    }
+#ifdef TS_PROFILE
+    if (mat == 0 && c.tid == 0)
+        printf("sy2sb wg prof (10 kcycles): qr %lld tfac %lld symm %lld w %lld syr2k %lld\n", tsp_t[1] / 10000,
+               tsp_t[2] / 10000, tsp_t[3] / 10000, tsp_t[4] / 10000, tsp_t[5] / 10000);
+#endif
+    __syncthreads();
+    s1_band_copy(a, slot, c.A, c.lda, c.tid, WARPS * 32);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // stage 2: band -> tridiagonal (bulge chasing)
@@ -1247,9 +1828,17 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
     const bool multi = em ? (em[0] == '1') : (nmat < 74);
     if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
-    const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob
+    // ARCB200_SY2SB_VARIANT=lockstep: the round-1 kernel (block barrier per tile step, per-thread
+    // cp.async) for A/B runs; default: decoupled warpgroups + TMA-unit bulk copies
+    const char *evv = getenv("ARCB200_SY2SB_VARIANT");
+    const bool lockstep = evv && evv[0] == 'l';
+    const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob (lockstep kernel only)
     const int warps = ev ? atoi(ev) : 8;
-    if (warps == 4) {
+    if (!lockstep) {
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)S1WG_SMEM_BYTES));
+        sy2sb_wg_kernel<<<nmat, 256, S1WG_SMEM_BYTES, st>>>(a);
+    } else if (warps == 4) {
         const size_t smem = (2 * 4 * 32 * 36 + 4608 + 3 * 1056 + 128) * sizeof(double);
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sy2sb_kernel<4><<<nmat, 128, smem, st>>>(a);

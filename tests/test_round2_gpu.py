@@ -303,7 +303,7 @@ def _nccl_worker(rank, world, port, q):
         calc.diagonalise(F, group=sweep.WORLD)
         y_sharded = np.array(calc.y)
         calc.diagonalise(F)                            # group=None: local, no collective
-        q.put((rank, float(np.abs(np.array(calc.y) - y_sharded).max()), y_sharded.shape))
+        q.put((rank, float(np.abs(np.array(calc.y) - y_sharded).max() / np.abs(y_sharded).max()), y_sharded.shape))
     finally:
         dist.destroy_process_group()
 
@@ -330,4 +330,4 @@ def test_sharded_sweep_two_gpus_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     for rank, err, shape in outs:
-        assert shape[0] == 11 and err == 0.0
+        assert shape[0] == 11 and err <= 1e-12      # batch-size dependent kernel configuration: rounding only
