@@ -84,6 +84,11 @@ int eig_sytrd(const EigSlots &S, int nmat, int cluster, cudaStream_t st, int *la
 // matrix is written to d_sel0 and only those eigenvector columns of Q1 are valid.
 int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches, int sel_k = 0,
               double sigma = 0.0, int32_t *d_sel0 = nullptr);
+// stage 2 for pair sweeps with k << N (eig_stein.cu): the k eigenpairs nearest sigma by bisection +
+// inverse iteration; eigenvalues land in oLam[0..k), eigenvectors of T in Q1 columns 0..k-1,
+// d_sel0[mat] = 0.  eig_stein_usable: k small enough for the work arrays (4 N k doubles in Q2).
+int eig_stein_usable(int N, int k);
+int eig_stein(const EigSlots &S, int nmat, int k, double sigma, int32_t *d_sel0, cudaStream_t st, int *launches);
 // stage 3: Z = Q_house * Q1[:, sel0 : sel0+nsel]  (in place on Q1 columns)
 int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,
               int *launches);

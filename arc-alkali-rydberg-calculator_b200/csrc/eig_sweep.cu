@@ -5,7 +5,8 @@
 //             H(R) = diag(h0) + sum_o M_o / (R 1e-6)^(3+o)   (calculations_atom_pairstate.py:3435-3440)
 //             written straight into the eigensolver's batch workspace (lower-triangle
 //             32x32 tiles only, coalesced; V / M_o are read through L2 once per batch)
-//   solve     eig_sytrd -> eig_stedc -> [select k nearest sigma] -> eig_ormtr
+//   solve     eig_sytrd | eig_sy2sb + eig_sb2st -> eig_stedc (all eigenpairs) | eig_stein (k nearest sigma)
+//             -> eig_ormtr | eig_q2_apply
 //   epilogue  y, highlight and the top-k composition per eigenvector, so eigenvectors
 //             never leave the GPU (calculations_atom_single.py:988-1021, 1395-1416;
 //             calculations_atom_pairstate.py:3494-3520).
@@ -384,7 +385,10 @@ int solve_batch(const WorkView &W, int nmat, int nsel, bool window, double sigma
         rc = eig_sytrd(W.S, nmat, eig_pick_cluster(L.N, nmat), st, launches);
     }
     if (rc) return rc;
-    rc = eig_stedc(W.S, nmat, st, launches, window ? nsel : 0, sigma, window ? W.sel0 : nullptr);
+    if (window && nsel < L.N && eig_stein_usable(L.N, nsel))
+        rc = eig_stein(W.S, nmat, nsel, sigma, W.sel0, st, launches);      // k << N: bisection + inverse iteration
+    else
+        rc = eig_stedc(W.S, nmat, st, launches, window ? nsel : 0, sigma, window ? W.sel0 : nullptr);
     if (rc) return rc;
     const int32_t *sel = window ? W.sel0 : nullptr;
     if (L.two_stage) {
