@@ -797,7 +797,14 @@ static __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsi
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+static __device__ __forceinline__ void cp_async_mbar_arrive(void *bar)
+{
+    // the barrier tracks the completion of this thread's earlier cp.async copies (SASS ARRIVES.LDGSTSBAR)
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 static __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// all state spaces: generic-proxy writes to GLOBAL memory (panels, tiles) before bulk copies read them
+static __device__ __forceinline__ void fence_async_proxy_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 static __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory"); }
 
 struct S1Wg {                      // warpgroup-private state of the decoupled phases
@@ -823,7 +830,7 @@ static __device__ __forceinline__ void s1_symm_wg(const S1Ctx &c, const S1Wg &g,
     const int ng = (nch + 3) >> 2;
     if (c.tid == 0) *g.next = 0;
     __syncthreads();
-    fence_async_proxy();           // generic-proxy writes of the earlier phases before the bulk copies
+    fence_async_proxy_all();       // generic-proxy writes of the earlier phases before the bulk copies
     auto issue_tile = [&](int Ib, int Jb, int tb) {      // lane <-> tile column (256 contiguous bytes)
         if (lane == 0) mbar_expect_tx(&g.tbar[tb], 32 * 32 * 8);
         __syncwarp();
@@ -913,7 +920,8 @@ static __device__ __forceinline__ void s1_symm_wg(const S1Ctx &c, const S1Wg &g,
 // stays in registers, -V_I in the warp's second transit tile, W_J / V_J ([k][n]: row k = panel
 // column) are shared by the warpgroup, the C tile arrives one step ahead.  DMMA row (x, grp) <->
 // tile row 4 grp + x, so a lane's four rows are contiguous (128-bit shared loads, global stores).
-static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g, int p, unsigned &tph, unsigned &bph)
+static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g, int p, unsigned &tph, unsigned &bph,
+                                                   int Jcap = 1 << 30)
 {
     constexpr int TSTR = S1_TSTR;
     const int lane = c.lane, grp = c.grp, tig = c.tig, np = c.np, lda = c.lda, NB = c.NB;
@@ -926,7 +934,7 @@ static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g
     const int ng = (nch + 3) >> 2;
     if (c.tid == 0) *g.next = 0;
     __syncthreads();
-    fence_async_proxy();
+    fence_async_proxy_all();
     auto issue_tile = [&](int Ib, int Jb) {
         if (lane == 0) mbar_expect_tx(&g.tbar[0], 32 * 32 * 8);
         __syncwarp();
@@ -948,7 +956,7 @@ static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g
         const int g0 = Jt + 4 * (ng - 1 - tt_);
         const int I = g0 + g.wl;
         const bool act = I < NB;
-        const int Jmax = min(g0 + 3, NB - 1);
+        const int Jmax = min(min(g0 + 3, NB - 1), Jcap);      // Jcap = Jt: first block column only
         if (act) {
             issue_tile(I, Jt);
             // V_I: panel columns k = 0..31 (lane <-> k), rows 32 I .. 32 I + 31
@@ -1033,6 +1041,292 @@ static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g
             wg_bar(g.wg);
         }
     }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// look-ahead band reduction: the rank-2k update of panel p fused with the symmetric product of
+// panel p + 1
+// ------------------------------------------------------------------------------------------
+// The two tensor phases above are bound by HBM latency, not by the tensor pipe: every warp has one
+// 8 KB tile in flight, and at the DMMA rate they would move 4.6 TB/s (each stored tile is read twice by
+// the symmetric product and read + written by the update: 32 KB per 512 DMMAs).  Once block column
+// p + 1 of the trailing matrix has been updated, panel p + 1 can be factored BEFORE the rest of the
+// update of panel p, and every remaining tile then makes a single round trip:
+//     C' = C - V_I W_J^T - W_I V_J^T      (256 DMMAs)   -> stored by a TMA bulk copy from shared memory
+//     X'_I += C' V'_J                     (128 DMMAs)   registers of the row's warp
+//     X'_J += C'^T V'_I   (J < I)         (128 DMMAs)   -> red.global.add.f64 into the X' panel
+// 16 KB per 512 DMMAs.  Four compute warps (one per scheduler: a warp alone sustains the pipe's one DMMA
+// per 16 cycles) own one block row each -- -W_I in registers, -V_I, V'_I and a two-tile C ring in shared
+// memory; a producer warp streams the shared operands W_J, V_J, V'_J through a two-stage ring guarded
+// by full / empty mbarriers, so the compute warps never meet at a block barrier inside the pass.
+static __device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
+// Work split of the fused pass: compute warp w (0..3, one per scheduler) does nothing but wait for
+// its operands, issue DMMAs and shared-memory fragment traffic; helper warp 4 + w does the memory
+// side of the same block row: cp.async of the next C tiles (two ahead) and of the row operands,
+// the 128-bit global stores of the updated tiles (read back from shared memory), and a quarter of
+// the shared W_J / V_J / V'_J ring.  (A first version let the compute warps issue one
+// cp.async.bulk per tile column themselves: UBLKCP takes its addresses from uniform registers,
+// so the 32 per-lane copies of a tile are serialised in an ELECT / R2UR loop -- ~1500 cycles of
+// the only warp that feeds the tensor pipe of its scheduler, profiles/r02_sy2sb_fused_v1_*.)
+struct S1Fz {
+    double *Vc, *Wc;               // panel p: reflectors and W (np x 32, column-major)
+    double *Vn;                    // panel p + 1 reflectors
+    double *Xacc;                  // X' accumulation panel (zeroed by the caller)
+    double(*Bs3)[3][32][BSTR];     // [buf][W_J | V_J | V'_J][row][col]
+    double *tiles;                 // the block row's four tiles: C ring (2), -V_I, V'_I
+    unsigned long long *rb;        // the block row's barriers: cfull[2], cready[2], cdone[2], vfull, vfree
+    unsigned long long *full, *empty;   // [2] each: operand ring
+};
+enum { RB_CFULL = 0, RB_CREADY = 2, RB_CDONE = 4, RB_VFULL = 6, RB_VFREE = 7 };
+
+struct S1FzPhase {                 // phase parities, persistent over the passes (one bit per barrier)
+    unsigned rb;                   // bits RB_*
+    unsigned ring;                 // bit buf: full (compute warps) / empty (helpers)
+};
+
+static __device__ __forceinline__ void s1_fused_pass(const S1Ctx &c, const S1Fz &f, int p, S1FzPhase &ph)
+{
+    constexpr int TSTR = S1_TSTR;
+    const int lane = c.lane, grp = c.grp, tig = c.tig, np = c.np, lda = c.lda, NB = c.NB;
+    const int w = c.wid & 3;
+    const bool helper = c.wid >= 4;
+    double *A = c.A;
+    const int J0 = p + 2;                  // first block row / column of the pass
+    const int ng = (NB - J0 + 3) >> 2;
+    double *Tc0 = f.tiles, *Tv = f.tiles + 2 * (32 * TSTR), *Tn = f.tiles + 3 * (32 * TSTR);
+    auto rbwait = [&](int which) {
+        mbar_wait(&f.rb[which], (ph.rb >> which) & 1u);
+        ph.rb ^= 1u << which;
+    };
+    // the schedule both warps of a block row walk through: groups of four block rows, largest first
+    auto group_g0 = [&](int t) { return J0 + 4 * (ng - 1 - t); };
+    auto row_of = [&](int t) { return group_g0(t) + ((t & 1) ? 3 - w : w); };    // alternate long and short rows
+    __syncthreads();
+    if (helper) {
+        // ------------------------------------------------------------------ memory side of block row w
+        auto load_tile = [&](double *dst, const double *src, size_t pitch) {     // 32 x 32 tile, columns `pitch` apart
+            const double *s0 = src + (size_t)(lane >> 4) * pitch + (lane & 15) * 2;
+            double *d0 = dst + (lane >> 4) * TSTR + (lane & 15) * 2;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                cp_async16_t(d0, s0);
+                s0 += 2 * pitch;
+                d0 += 2 * TSTR;
+            }
+        };
+        auto fill_ring = [&](int buf, int J) {           // this helper's quarter: rows 8 w .. 8 w + 7 of the three tiles
+            const int k0 = 8 * w + (lane >> 4), cc = (lane & 15) * 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + 2 * q;
+                cp_async16_t(&f.Bs3[buf][0][k][cc], f.Wc + (size_t)k * np + 32 * J + cc);
+                cp_async16_t(&f.Bs3[buf][1][k][cc], f.Vc + (size_t)k * np + 32 * J + cc);
+                cp_async16_t(&f.Bs3[buf][2][k][cc], f.Vn + (size_t)k * np + 32 * J + cc);
+            }
+            cp_async_mbar_arrive(&f.full[buf]);
+        };
+        // look-ahead iterator over the steps of the pass (for the ring fills two steps ahead)
+        int ft = 0, fJ = J0;                              // next step to fill
+        auto fill_next = [&](int buf) {
+            if (ft < ng) {
+                fill_ring(buf, fJ);
+                if (++fJ > min(group_g0(ft) + 3, NB - 1)) { ++ft; fJ = J0; }
+            }
+        };
+        fill_next(0);
+        fill_next(1);
+        int s = 0;
+        for (int t = 0; t < ng; ++t) {
+            const int I = row_of(t);
+            const bool act = I < NB;
+            const int Jlast = min(group_g0(t) + 3, NB - 1);
+            if (act) {
+                load_tile(Tv, f.Vc + 32 * I, np);         // V_I  as [k][row]
+                load_tile(Tn, f.Vn + 32 * I, np);         // V'_I as [n][k]
+                cp_async_mbar_arrive(&f.rb[RB_VFULL]);
+                load_tile(Tc0, A + (size_t)(32 * J0) * lda + 32 * I, lda);
+                cp_async_mbar_arrive(&f.rb[RB_CFULL + 0]);
+                if (J0 + 1 <= I) {
+                    load_tile(Tc0 + 32 * TSTR, A + (size_t)(32 * (J0 + 1)) * lda + 32 * I, lda);
+                    cp_async_mbar_arrive(&f.rb[RB_CFULL + 1]);
+                }
+            }
+            for (int J = J0; J <= Jlast; ++J, ++s) {
+                if (act && J <= I) {
+                    const int cb = (J - J0) & 1;
+                    double *tile = Tc0 + cb * (32 * TSTR);
+                    // the updated tile: shared memory -> global, 256-byte column segments
+                    rbwait(RB_CREADY + cb);
+                    {
+                        const double *s0 = tile + (lane >> 4) * TSTR + (lane & 15) * 2;
+                        double *d0 = A + (size_t)(32 * J + (lane >> 4)) * lda + 32 * I + (lane & 15) * 2;
+#pragma unroll 4
+                        for (int k = 0; k < 16; ++k) {
+                            *reinterpret_cast<double2 *>(d0) = *reinterpret_cast<const double2 *>(s0);
+                            s0 += 2 * TSTR;
+                            d0 += 2 * (size_t)lda;
+                        }
+                    }
+                    // the compute warp is done with the tile: refill its buffer two tiles ahead
+                    rbwait(RB_CDONE + cb);
+                    if (J + 2 <= I) {
+                        load_tile(tile, A + (size_t)(32 * (J + 2)) * lda + 32 * I, lda);
+                        cp_async_mbar_arrive(&f.rb[RB_CFULL + cb]);
+                    }
+                }
+                // operand ring: all four compute warps are done with step s -> its buffer gets step s + 2
+                const int buf = s & 1;
+                mbar_wait(&f.empty[buf], (ph.ring >> buf) & 1u);
+                ph.ring ^= 1u << buf;
+                fill_next(buf);
+            }
+            if (act) rbwait(RB_VFREE);                    // row operands may be overwritten
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else {
+        // ------------------------------------------------------------------ compute warp w
+        int s = 0;
+        for (int t = 0; t < ng; ++t) {
+            const int I = row_of(t);
+            const bool act = I < NB;
+            const int Jlast = min(group_g0(t) + 3, NB - 1);
+            double fw[4][8];
+            double xa[4][4][2];
+            if (act) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double2 *pw2 = reinterpret_cast<const double2 *>(f.Wc + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                    const double2 w0 = pw2[0], w1 = pw2[1];
+                    fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) xa[x][y][0] = xa[x][y][1] = 0.0;
+                rbwait(RB_VFULL);
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) Tv[lane * TSTR + r] = -Tv[lane * TSTR + r];
+                __syncwarp();
+            }
+            const double *tv = Tv + tig * TSTR + 4 * grp;
+            for (int J = J0; J <= Jlast; ++J, ++s) {
+                const int buf = s & 1;
+                mbar_wait(&f.full[buf], (ph.ring >> buf) & 1u);
+                ph.ring ^= 1u << buf;
+                if (act && J <= I) {
+                    const int cb = (J - J0) & 1;
+                    double *tile = Tc0 + cb * (32 * TSTR);
+                    rbwait(RB_CFULL + cb);
+                    double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
+                    double *tc = tile + (2 * tig) * TSTR + 4 * grp;
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
+                        const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
+                        const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                        c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
+                        c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
+                    }
+                    // ---- C' = C - V_I W_J^T - W_I V_J^T
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
+                        const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
+                        const double fv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const double bw = f.Bs3[buf][0][4 * ks + tig][8 * y + grp];
+                            const double bv = f.Bs3[buf][1][4 * ks + tig][8 * y + grp];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+                                dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
+                            }
+                        }
+                    }
+                    // ---- C' back into the tile: the helper stores it, the products below read it
+                    __syncwarp();
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        double2 *o0 = reinterpret_cast<double2 *>(tc + 8 * y * TSTR);
+                        double2 *o1 = reinterpret_cast<double2 *>(tc + (8 * y + 1) * TSTR);
+                        o0[0] = make_double2(c0[0][y], c0[1][y]);
+                        o0[1] = make_double2(c0[2][y], c0[3][y]);
+                        o1[0] = make_double2(c1[0][y], c1[1][y]);
+                        o1[1] = make_double2(c1[2][y], c1[3][y]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&f.rb[RB_CREADY + cb]);
+                    // ---- X'_I += C' V'_J
+                    {
+                        const double *pd = tile + tig * TSTR + grp;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            double fa[4];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) {
+                                const double b = f.Bs3[buf][2][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) dmma_t(xa[x][y][0], xa[x][y][1], fa[x], b);
+                            }
+                        }
+                    }
+                    // ---- X'_J += C'^T V'_I (strictly lower tiles)
+                    if (J < I) {
+                        double ya[4][4][2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) ya[x][y][0] = ya[x][y][1] = 0.0;
+                        const double *pt = tile + grp * TSTR + tig;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            double fa[4];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) {
+                                const double b = Tn[(8 * y + grp) * TSTR + 4 * ks + tig];
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) dmma_t(ya[x][y][0], ya[x][y][1], fa[x], b);
+                            }
+                        }
+                        double *xr = f.Xacc + (size_t)(2 * tig) * np + 32 * J + grp;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) atomicAdd(xr + (size_t)(8 * y + h) * np + 8 * x, ya[x][y][h]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&f.rb[RB_CDONE + cb]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&f.empty[buf]);
+            }
+            if (act) {
+                double *xr = f.Xacc + (size_t)(2 * tig) * np + 32 * I + grp;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) atomicAdd(xr + (size_t)(8 * y + h) * np + 8 * x, xa[x][y][h]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&f.rb[RB_VFREE]);
+            }
+        }
+    }
+    __threadfence();               // tile stores and reductions are performed before the block reads them
     __syncthreads();
 }
 
@@ -1797,6 +2091,113 @@ __global__ void __launch_bounds__(OTW * 32, 1) ormtr_t_kernel(TsArgs a)
 }
 
 
+// Look-ahead kernel (default for batches of whole-SM matrices): per panel p
+//   (A) rank-2k update of block column p + 1 only      (s1_syr2k_wg, both warpgroups)
+//   (B) panel QR + T factor of panel p + 1
+//   (C) fused pass over the remaining tiles: update with panel p, X' = A22 V' of panel p + 1
+//   (D) W' = X' T' - 1/2 V' (T'^T V'^T X' T')
+// The panels alternate between two buffer pairs; X' is accumulated with global reductions in a
+// third panel and copied (L2 loads) into the W buffer of panel p + 1.
+constexpr size_t S1FZ_SMEM_BYTES = (size_t)(2 * 8 * 32 * S1_TSTR + 2 * 4608 + 128) * sizeof(double) + 640;
+__global__ void __launch_bounds__(256, 1) sy2sb_fused_kernel(TsArgs a)
+{
+    constexpr int WARPS = 8;
+    constexpr int TSTR = S1_TSTR;
+    constexpr int TILES = 2 * WARPS * 32 * TSTR;
+    const int mat = blockIdx.x;
+    double *slot = a.base + (size_t)mat * a.slot;
+    extern __shared__ double sm[];
+    const int np = a.Npad, NB = a.NB;
+    S1Ctx c;
+    c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
+    c.np = np; c.lda = np; c.NB = NB;
+    c.A = slot + a.oA; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
+    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+    double *bsB = sm + TILES + 4608;
+    c.Ts = reinterpret_cast<double(*)[33]>(bsB);
+    c.G = reinterpret_cast<double(*)[33]>(bsB + 1056);
+    c.M1 = reinterpret_cast<double(*)[33]>(bsB + 2 * 1056);
+    double *small = sm + TILES + 2 * 4608;
+    c.wv = reinterpret_cast<double(*)[32]>(small);
+    c.sred = reinterpret_cast<double(*)[16]>(small + 64);
+    c.taus = small + 96;
+    c.Tw = sm + c.wid * (2 * 32 * TSTR);
+    // barriers: 16 tile + 4 warpgroup operand (TMA phases); fused pass: 4 block rows x 8, 2 full + 2 empty
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(small + 128);
+    int *ctl = reinterpret_cast<int *>(bars + 56);
+    S1Wg g;
+    g.wg = c.wid >> 2; g.wl = c.wid & 3;
+    g.Bs = g.wg ? reinterpret_cast<double(*)[2][32][BSTR]>(bsB) : c.Bs;
+    g.tbar = bars + 2 * c.wid;
+    g.bbar = bars + 16 + 2 * g.wg;
+    g.next = ctl;
+    g.cur = ctl + 1 + g.wg;
+    if (c.tid == 0) {
+        for (int i = 0; i < 20; ++i) mbar_init(&bars[i], 1);
+        for (int r = 0; r < 4; ++r) {
+            unsigned long long *rb = bars + 20 + 8 * r;
+            mbar_init(&rb[RB_CFULL], 32); mbar_init(&rb[RB_CFULL + 1], 32);      // cp.async arrivals of the helper's lanes
+            mbar_init(&rb[RB_CREADY], 1); mbar_init(&rb[RB_CREADY + 1], 1);
+            mbar_init(&rb[RB_CDONE], 1); mbar_init(&rb[RB_CDONE + 1], 1);
+            mbar_init(&rb[RB_VFULL], 32); mbar_init(&rb[RB_VFREE], 1);
+        }
+        mbar_init(&bars[52], 128); mbar_init(&bars[53], 128);                    // full: 4 helpers x 32 lanes
+        mbar_init(&bars[54], 4); mbar_init(&bars[55], 4);                        // empty: the four compute warps
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    fence_async_proxy();
+    __syncthreads();
+    // panel buffers: even panels in (oVp, oWp), odd panels in the (idle) eigenvector matrix
+    double *Vb[2] = {slot + a.oVp, slot + a.oZ};
+    double *Wb[2] = {slot + a.oWp, slot + a.oZ + (size_t)32 * np};
+    double *Xacc = slot + a.oZ + (size_t)64 * np;
+    S1Fz f;
+    f.Xacc = Xacc;
+    f.Bs3 = reinterpret_cast<double(*)[3][32][BSTR]>(sm + TILES);
+    f.tiles = sm + (c.wid & 3) * (4 * 32 * TSTR);
+    f.rb = bars + 20 + 8 * (c.wid & 3);
+    f.full = bars + 52;
+    f.empty = bars + 54;
+    unsigned tph = 0, bph = 0;
+    S1FzPhase fph;
+    fph.rb = 0; fph.ring = 0;
+    auto reload_T = [&](int p) {
+        for (int t = c.tid; t < 1024; t += WARPS * 32) c.Ts[t >> 5][t & 31] = c.Tfac[(size_t)p * 1024 + t];
+    };
+    // ---- panel 0: QR, T, X = A22 V (two reads of the lower triangle, once), W
+    c.Vp = Vb[0]; c.Wp = Wb[0];
+    s1_panel_qr<WARPS>(c, 0);
+    s1_tfactor<WARPS>(c, 0);
+    s1_symm_wg(c, g, 0, tph, bph);
+    reload_T(0);
+    s1_wphase<WARPS>(c, 0);
+    for (int p = 0; p < NB - 1; ++p) {
+        const bool last = (p == NB - 2);
+        double *Vn = Vb[(p + 1) & 1], *Wn = Wb[(p + 1) & 1];
+        if (!last) {
+            // X' accumulator of the rows below the next panel's band
+            for (int n = 0; n < 32; ++n)
+                for (int r = 32 * (p + 2) + c.tid; r < np; r += WARPS * 32) Xacc[(size_t)n * np + r] = 0.0;
+            __threadfence();
+        }
+        c.Vp = Vb[p & 1]; c.Wp = Wb[p & 1];
+        s1_syr2k_wg(c, g, p, tph, bph, p + 1);                       // (A)
+        if (last) break;
+        c.Vp = Vn; c.Wp = Wn;
+        s1_panel_qr<WARPS>(c, p + 1);                                // (B)
+        s1_tfactor<WARPS>(c, p + 1);
+        f.Vc = Vb[p & 1]; f.Wc = Wb[p & 1]; f.Vn = Vn;
+        s1_fused_pass(c, f, p, fph);                                 // (C)
+        for (int n = 0; n < 32; ++n)                                 // (D)
+            for (int r = 32 * (p + 2) + c.tid; r < np; r += WARPS * 32) Wn[(size_t)n * np + r] = __ldcg(&Xacc[(size_t)n * np + r]);
+        reload_T(p + 1);
+        s1_wphase<WARPS>(c, p + 1);
+    }
+    __syncthreads();
+    s1_band_copy(a, slot, c.A, c.lda, c.tid, WARPS * 32);
+}
+
+
 TsArgs make_args(const EigSlots &S)
 {
     const EigLayout &L = S.L;
@@ -1828,13 +2229,23 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
     const bool multi = em ? (em[0] == '1') : (nmat < 74);
     if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
-    // ARCB200_SY2SB_VARIANT=lockstep: the round-1 kernel (block barrier per tile step, per-thread
-    // cp.async) for A/B runs; default: decoupled warpgroups + TMA-unit bulk copies
+    // Three kernels, measured on C3 (N = 2363, 296 matrices; profiles/r02_ab_sy2sb_variants_c3.json):
+    //   lockstep (default)  312 ms   block barrier per tile step, per-thread cp.async
+    //   wg                  320 ms   decoupled warpgroups, TMA-unit bulk copies + mbarriers
+    //                       (309 ms with per-thread cp.async tracked by the same mbarriers: the decoupling is
+    //                       worth 1 %, the ELECT / R2UR serialisation of one UBLKCP per tile column costs 3.5 %)
+    //   fused               392 ms   look-ahead: rank-2k update fused with the next symmetric product
+    // ARCB200_SY2SB_VARIANT = lockstep | wg | fused selects one.
     const char *evv = getenv("ARCB200_SY2SB_VARIANT");
-    const bool lockstep = evv && evv[0] == 'l';
+    const bool wgonly = evv && evv[0] == 'w';
+    const bool fusedk = evv && evv[0] == 'f';
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob (lockstep kernel only)
     const int warps = ev ? atoi(ev) : 8;
-    if (!lockstep) {
+    if (fusedk) {
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)S1FZ_SMEM_BYTES));
+        sy2sb_fused_kernel<<<nmat, 256, S1FZ_SMEM_BYTES, st>>>(a);
+    } else if (wgonly) {
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)S1WG_SMEM_BYTES));
         sy2sb_wg_kernel<<<nmat, 256, S1WG_SMEM_BYTES, st>>>(a);
