@@ -12,13 +12,13 @@
 //                        D&C path: ties go to the lower eigenvalue) -> lam[0..k), sel0 = 0
 //   stein_invit_kernel   one thread per eigenvector: LU with partial pivoting of T - lam I (dgttrf
 //                        row interchanges, reciprocal pivots, tiny pivots perturbed to eps |T| like
-//                        dlagts), three inverse iterations from a random vector; factors and the
+//                        dlagts), two inverse iterations from a random vector; factors and the
 //                        iterate live in global memory interleaved over the eigenvectors, so the
 //                        32 lanes of a warp stream 256 contiguous bytes per array and row
-//   stein_orth_kernel    eigenvalues closer than 1e-6 |T| form a cluster; one warp per cluster
+//   stein_orth_kernel    eigenvalues closer than 1e-6 |T| form a cluster; one CTA per cluster
 //                        re-orthogonalises its vectors (modified Gram-Schmidt, twice).  Outside
 //                        clusters three iterations leave a cross contamination below
-//                        (eps |T| / gap)^3 < 1e-26.
+//                        (eps |T| / gap)^2 < 1e-17.
 // Measured on the C3 tridiagonals (N = 2363, k = 250, numpy model of this file): eigenvalues
 // 4e-16 |T|, residual 4e-16 |T|, orthogonality 1e-12, highlight identical to LAPACK to 3e-15.
 #include <math.h>
@@ -28,7 +28,7 @@
 namespace {
 
 constexpr double STEIN_CLUSTER_TOL = 1e-6;
-constexpr int STEIN_ITS = 3;
+constexpr int STEIN_ITS = 2;      // eigenvalues are exact to eps |T|: the second iteration already converges (dstein)
 
 struct SteinArgs {
     int N, Npad, k, kp;
@@ -86,11 +86,38 @@ __global__ void __launch_bounds__(32) stein_prep_kernel(SteinArgs a)
     gl -= 2.0 * tn * eps * n + 2.0 * pivmin;
     gu += 2.0 * tn * eps * n + 2.0 * pivmin;
     __syncwarp();
+    // radius search: the smallest rho (to ~1e-7 of the spectral width) with at least k eigenvalues in
+    // (sigma - rho, sigma + rho); 16-section per round, lanes 0-15 count below sigma - rho_i, lanes
+    // 16-31 below sigma + rho_i.  The candidates for the bisection are the eigenvalues in that interval.
+    double rlo = 0.0, rhi = fmax(gu - a.sigma, a.sigma - gl);
+    int cL = 0, cR = n;                                    // counts at sigma -+ rhi
+    for (int round = 0; round < 6; ++round) {
+        const int i = lane & 15;
+        const double rho = rlo + (rhi - rlo) * (double)(i + 1) / 17.0;
+        const double x = (lane < 16) ? a.sigma - rho : a.sigma + rho;
+        const int cnt = sturm_count(d, e2, n, x, pivmin);
+        const int cl = __shfl_sync(ARCB200_FULL_MASK, cnt, i), cr = __shfl_sync(ARCB200_FULL_MASK, cnt, 16 + i);
+        const unsigned ok = __ballot_sync(ARCB200_FULL_MASK, lane < 16 && (cr - cl) >= a.k);
+        // first radius that holds k eigenvalues (if any) bounds from above, its predecessor from below
+        const int first = ok ? __ffs(ok) - 1 : 16;
+        const double nlo = (first == 0) ? rlo : rlo + (rhi - rlo) * (double)first / 17.0;
+        if (first < 16) {
+            const double nhi = rlo + (rhi - rlo) * (double)(first + 1) / 17.0;
+            cL = __shfl_sync(ARCB200_FULL_MASK, cl, first);
+            cR = __shfl_sync(ARCB200_FULL_MASK, cr, first);
+            rhi = nhi;
+        }
+        rlo = nlo;
+    }
     if (lane == 0) {
-        const int lo = sturm_count(d, e2, n, a.sigma, pivmin);      // eigenvalues below sigma
-        const int c0 = max(0, lo - a.k), c1 = min(n, lo + a.k);
+        int c0 = cL, nc = cR - cL;
+        if (nc < a.k || nc > 2 * a.k) {                    // (massively degenerate boundary: plain index window)
+            const int lo = sturm_count(d, e2, n, a.sigma, pivmin);
+            c0 = max(0, lo - a.k);
+            nc = min(n, lo + a.k) - c0;
+        }
         aux[SA_TN] = tn; aux[SA_PIVMIN] = pivmin; aux[SA_GL] = gl; aux[SA_GU] = gu;
-        aux[SA_C0] = (double)c0; aux[SA_NCAND] = (double)(c1 - c0);
+        aux[SA_C0] = (double)c0; aux[SA_NCAND] = (double)nc;
     }
 }
 
@@ -119,7 +146,7 @@ __global__ void __launch_bounds__(128) stein_bisect_kernel(SteinArgs a)
         int cnt = q < 0.0;
         for (int i = 1; i < n; ++i) {
             if (fabs(q) < pivmin) q = -pivmin;
-            q = d[i] - mid - e2[i - 1] / q;
+            q = d[i] - mid - e2[i - 1] * __drcp_rn(q);     // sign sequence only: a rounded reciprocal is enough
             cnt += q < 0.0;
         }
         if (cnt > idx) hi = mid; else lo = mid;
@@ -240,13 +267,12 @@ __global__ void __launch_bounds__(128) stein_invit_kernel(SteinArgs a)
     }
 }
 
-// grid = (ceil(k / 4), nmat), 4 warps per CTA; warp <-> eigenvector j, only cluster heads work
+// grid = (k, nmat), 128 threads; CTA <-> eigenvector j, only the heads of clusters work
 __global__ void __launch_bounds__(128) stein_orth_kernel(SteinArgs a, int32_t *status)
 {
     const int mat = blockIdx.y;
-    const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (j >= a.k) return;
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *slot = a.base + (size_t)mat * a.slot;
     const double *lam = slot + a.oLam;
     const double tol = STEIN_CLUSTER_TOL * (slot + a.oAux)[SA_TN];
@@ -254,8 +280,16 @@ __global__ void __launch_bounds__(128) stein_orth_kernel(SteinArgs a, int32_t *s
     int end = j + 1;
     while (end < a.k && lam[end] - lam[end - 1] <= tol) ++end;
     if (end == j + 1) return;                                  // isolated eigenvalue
+    __shared__ double red[4];
     double *Z = slot + a.oZ;
     const int n = a.N;
+    auto block_sum = [&](double v) {
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) red[wid] = v;
+        __syncthreads();
+        return (red[0] + red[1]) + (red[2] + red[3]);
+    };
     for (int m = j + 1; m < end; ++m) {
         double *zm = Z + (size_t)m * a.Npad;
         double first = 1.0;
@@ -263,21 +297,19 @@ __global__ void __launch_bounds__(128) stein_orth_kernel(SteinArgs a, int32_t *s
             for (int q = j; q < m; ++q) {
                 const double *zq = Z + (size_t)q * a.Npad;
                 double dot = 0.0;
-                for (int i = lane; i < n; i += 32) dot += zq[i] * zm[i];
-                dot = warp_sum(dot);
-                for (int i = lane; i < n; i += 32) zm[i] -= dot * zq[i];
-                __syncwarp();
+                for (int i = tid; i < n; i += 128) dot += zq[i] * zm[i];
+                dot = block_sum(dot);
+                for (int i = tid; i < n; i += 128) zm[i] -= dot * zq[i];
             }
             double nn = 0.0;
-            for (int i = lane; i < n; i += 32) nn += zm[i] * zm[i];
-            nn = sqrt(warp_sum(nn));
+            for (int i = tid; i < n; i += 128) nn += zm[i] * zm[i];
+            nn = sqrt(block_sum(nn));
             if (rep == 0) first = nn;
             const double rn = 1.0 / fmax(nn, 1e-300);
-            for (int i = lane; i < n; i += 32) zm[i] *= rn;
-            __syncwarp();
+            for (int i = tid; i < n; i += 128) zm[i] *= rn;
         }
         // two vectors of a cluster came out (nearly) parallel: reported, never silently wrong
-        if (first < 1e-6 && lane == 0 && status) atomicAdd(&status[mat], 1);
+        if (first < 1e-6 && tid == 0 && status) atomicAdd(&status[mat], 1);
     }
 }
 
@@ -312,7 +344,7 @@ int eig_stein(const EigSlots &S, int nmat, int k, double sigma, int32_t *d_sel0,
     stein_bisect_kernel<<<dim3((2 * k + 127) / 128, nmat), 128, 0, st>>>(a);
     stein_window_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(a, nmat);
     stein_invit_kernel<<<dim3((a.kp + 127) / 128, nmat), 128, 0, st>>>(a);
-    stein_orth_kernel<<<dim3((k + 3) / 4, nmat), 128, 0, st>>>(a, nullptr);
+    stein_orth_kernel<<<dim3(k, nmat), 128, 0, st>>>(a, nullptr);
     ARCB200_LAUNCH_CHECK("stein kernels");
     if (launches) *launches += 5;
     return 0;
