@@ -524,7 +524,17 @@ def bench_c2(args):
     t_num = float(np.mean([t[0] for t in times[2:]]))
     t_int = float(np.mean([t[1] for t in times[2:]]))
     lens = rb.lengths.astype(np.int64)
-    ptpairs = np.minimum(lens[pairs[:, 0]], lens[pairs[:, 1]]).sum()
+    up = np.minimum(lens[pairs[:, 0]], lens[pairs[:, 1]])
+    ptpairs = up.sum()
+    # bytes the kernel requests from L2: per pair 8 B per grid point for psi_b, plus, per run of pairs
+    # sharing state a, 16 B per grid point for psi_a and its r grid (24 B per point and pair without runs)
+    runs = radial.split_runs(pairs)
+    if runs is None:
+        l2_bytes, mean_run = 24.0 * ptpairs, 1.0
+    else:
+        rs, rl = runs
+        l2_bytes = 8.0 * ptpairs + 16.0 * np.maximum.reduceat(up, rs).sum()
+        mean_run = float(rl.mean())
     # tensor-core Gram form of the same table (opt-in atom.fast_radial)
     gram = None
     try:
@@ -544,7 +554,7 @@ def bench_c2(args):
         gram = {"error": repr(ex)[:200]}
     sm_mhz = peaks_raw().get("sm_max_mhz", 1965.0)
     l2_peak = L2_BYTES_PER_CLK * sm_mhz * 1e6 / 1e9
-    ach = ptpairs * 24.0 / (t_int * 1e-3) / 1e9
+    ach = l2_bytes / (t_int * 1e-3) / 1e9
     # cpu baseline: oracle on a random sample of pairs
     from oracle import oracle
     rng = np.random.default_rng(0)
@@ -569,11 +579,13 @@ def bench_c2(args):
             "metric": "radial_matrix_elements_per_sec", "value": len(pairs) / ((t_num + t_int) * 1e-3),
             "unit": "elements/s", "ms_numerov": t_num, "ms_integrals": t_int, "gpu_launches": 2,
             "max_rel_err_vs_cpu_sample": worst, "gram_path": gram,
-            "roofline": {"bound": "l2", "kernel": "radial_integral_kernel", "achieved": ach, "peak": l2_peak,
+            "roofline": {"bound": "l2", "kernel": "radial_integral_runs_kernel", "achieved": ach, "peak": l2_peak,
                          "unit": "GB/s", "frac": ach / l2_peak, "traffic": load_traffic("radial_integral_c2"),
                          "peak_source": "L2->SM cap 6300 B/clk (B300_MICROARCH.md, measured on B300) x %.0f MHz; the "
                                         "wavefunctions (7.1 GB) are re-read ~450x from L2, HBM sees each once" % sm_mhz,
-                         "note": "24 B per grid point per pair (two psi + one r grid) served by L2"},
+                         "mean_pairs_per_run": mean_run, "l2_bytes_requested": l2_bytes,
+                         "note": "psi_b per pair + psi_a and r_a once per run of <= 8 pairs sharing state a "
+                                 "(24 B per grid point and pair without runs), served by L2"},
             "cpu_baseline": {"value": len(sample) / dt, "unit": "elements/s", "cores": 1,
                              "kind": "reference" if oracle.have_ref() else "port",
                              "sample": "%d random pairs of the table, 2 Numerov runs + trapezoid each" % len(sample)}}

@@ -34,7 +34,9 @@ def c2_workload(atom, nmin=20, nmax=120, lmax=20):
             swap = E[a] > E[b]
             lo, hi = np.where(swap, b, a), np.where(swap, a, b)
             pairs.append(np.stack([lo, hi, np.full_like(lo, power)], axis=1))
-    return states, np.concatenate(pairs).astype(np.int32)
+    pairs = np.concatenate(pairs).astype(np.int32)
+    # the table sorted by (power, lower-energy state, partner): consecutive pairs share psi_a
+    return states, pairs[np.lexsort((pairs[:, 1], pairs[:, 0], pairs[:, 2]))]
 
 
 def c2_blocks(atom, nmin=20, nmax=120, lmax=20):
