@@ -38,7 +38,6 @@ _SIGNATURES = {
                                             c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_radial_integrals": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_vp]),
-    "arcb200_radial_integrals_runs": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_radial_gram": (c_int, [c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                     c_i32, c_vp, c_vp, c_i32, c_i32, c_i32]),
     "arcb200_semiclassical_table": (c_int, [c_int, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,

@@ -291,7 +291,7 @@ class AlkaliAtom:
             # collective: every rank of the group builds the same table
             vals = rb.integrals_sharded(pair_rows, self.radial_group).cpu().numpy()
         elif not self.fast_radial or len(todo) < self.gram_threshold:
-            # sorted by (power, lower-energy state): runs of pairs sharing psi_a go to the run kernel
+            # sorted by (power, lower-energy state): the warps of a CTA share psi_a / r_a through L1
             order = np.lexsort((pair_rows[:, 1], pair_rows[:, 0], pair_rows[:, 2]))
             vals = np.empty(len(todo))
             vals[order] = rb.integrals(pair_rows[order])

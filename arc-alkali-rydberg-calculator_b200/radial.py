@@ -34,26 +34,6 @@ def make_state(innerLimit, outerLimit, step, init1, init2, l, s, j, stateEnergy,
 GRAM_REFINE_THRESH = 1e-3
 
 
-def split_runs(pairs, run_max=8):
-    """Runs of consecutive pairs with the same (state a, power), cut into pieces of <= run_max:
-    (run_start int64[], run_len int32[]) for arcb200_radial_integrals_runs, or None when the list has
-    (almost) no such runs (an unsorted table) and the per-pair kernel is the better choice.  O(n)."""
-    n = len(pairs)
-    if n < 64:
-        return None
-    brk = np.flatnonzero((pairs[1:, 0] != pairs[:-1, 0]) | (pairs[1:, 2] != pairs[:-1, 2])) + 1
-    starts = np.concatenate(([0], brk))
-    if len(starts) > 0.6 * n:
-        return None
-    lens = np.diff(np.concatenate((starts, [n])))
-    nchunk = (lens + run_max - 1) // run_max
-    first = np.repeat(starts, nchunk)
-    inner = np.arange(nchunk.sum()) - np.repeat(np.cumsum(nchunk) - nchunk, nchunk)
-    run_start = (first + run_max * inner).astype(np.int64)
-    run_len = np.minimum(run_max, np.repeat(starts + lens, nchunk) - run_start).astype(np.int32)
-    return run_start, run_len
-
-
 def sharded_table(compute, pairs, group="world"):
     """One matrix-element table for all ranks of the process group: rank g evaluates the
     contiguous shard pairs[g*P/G:(g+1)*P/G] with `compute(shard) -> tensor[len(shard)]` and
@@ -142,17 +122,6 @@ class RadialBatch:
         dev = torch.device("cuda", self.device)
         d_pairs = torch.from_numpy(pairs).to(dev)
         out = torch.empty(len(pairs), dtype=torch.float64, device=dev)
-        runs = split_runs(pairs)
-        if runs is not None:
-            run_start, run_len = runs
-            d_rs, d_rl = torch.from_numpy(run_start).to(dev), torch.from_numpy(run_len).to(dev)
-            rc = lib.arcb200_radial_integrals_runs(
-                self.device, _lib.stream_ptr(self.device), len(run_start), _lib.ptr(d_rs), _lib.ptr(d_rl),
-                _lib.ptr(d_pairs), _lib.ptr(self.d_states), _lib.ptr(self.d_offsets), _lib.ptr(self.d_psi),
-                _lib.ptr(self.d_r), _lib.ptr(out))
-            _lib.check(rc, "arcb200_radial_integrals_runs")
-            self.kernel_launches += 1
-            return out
         rc = lib.arcb200_radial_integrals(
             self.device, _lib.stream_ptr(self.device), len(pairs), _lib.ptr(d_pairs),
             _lib.ptr(self.d_states), _lib.ptr(self.d_offsets), _lib.ptr(self.d_psi),

@@ -526,15 +526,7 @@ def bench_c2(args):
     lens = rb.lengths.astype(np.int64)
     up = np.minimum(lens[pairs[:, 0]], lens[pairs[:, 1]])
     ptpairs = up.sum()
-    # bytes the kernel requests from L2: per pair 8 B per grid point for psi_b, plus, per run of pairs
-    # sharing state a, 16 B per grid point for psi_a and its r grid (24 B per point and pair without runs)
-    runs = radial.split_runs(pairs)
-    if runs is None:
-        l2_bytes, mean_run = 24.0 * ptpairs, 1.0
-    else:
-        rs, rl = runs
-        l2_bytes = 8.0 * ptpairs + 16.0 * np.maximum.reduceat(up, rs).sum()
-        mean_run = float(rl.mean())
+    l2_bytes = 24.0 * ptpairs          # two psi + one r grid per grid point and pair, served by L1 / L2
     # tensor-core Gram form of the same table (opt-in atom.fast_radial)
     gram = None
     try:
@@ -579,13 +571,12 @@ def bench_c2(args):
             "metric": "radial_matrix_elements_per_sec", "value": len(pairs) / ((t_num + t_int) * 1e-3),
             "unit": "elements/s", "ms_numerov": t_num, "ms_integrals": t_int, "gpu_launches": 2,
             "max_rel_err_vs_cpu_sample": worst, "gram_path": gram,
-            "roofline": {"bound": "l2", "kernel": "radial_integral_runs_kernel", "achieved": ach, "peak": l2_peak,
+            "roofline": {"bound": "l2", "kernel": "radial_integral_kernel", "achieved": ach, "peak": l2_peak,
                          "unit": "GB/s", "frac": ach / l2_peak, "traffic": load_traffic("radial_integral_c2"),
                          "peak_source": "L2->SM cap 6300 B/clk (B300_MICROARCH.md, measured on B300) x %.0f MHz; the "
                                         "wavefunctions (7.1 GB) are re-read ~450x from L2, HBM sees each once" % sm_mhz,
-                         "mean_pairs_per_run": mean_run, "l2_bytes_requested": l2_bytes,
-                         "note": "psi_b per pair + psi_a and r_a once per run of <= 8 pairs sharing state a "
-                                 "(24 B per grid point and pair without runs), served by L2"},
+                         "note": "24 B per grid point per pair (two psi + one r grid); the table is sorted by its "
+                                 "lower-energy state, so the warps of a CTA share psi_a / r_a through L1"},
             "cpu_baseline": {"value": len(sample) / dt, "unit": "elements/s", "cores": 1,
                              "kind": "reference" if oracle.have_ref() else "port",
                              "sample": "%d random pairs of the table, 2 Numerov runs + trapezoid each" % len(sample)}}

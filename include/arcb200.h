@@ -109,15 +109,6 @@ int arcb200_radial_integrals(int device, void *stream, int64_t npairs,
                              const int64_t *d_offsets, const double *d_psi,
                              const double *d_r, double *d_out);
 
-/* The same integrals for a pair list in which consecutive pairs often share state a and the power (a table
- * sorted by its lower-energy state): run r covers pairs [d_run_start[r], d_run_start[r] + d_run_len[r]),
- * 1 <= len <= 8, all with the same a and power; one warp per run reads psi_a / r_a once.  Results are
- * bit-identical to arcb200_radial_integrals (same per-pair summation order); d_out is indexed like d_pairs. */
-int arcb200_radial_integrals_runs(int device, void *stream, int64_t nruns, const int64_t *d_run_start,
-                                  const int32_t *d_run_len, const int32_t *d_pairs,
-                                  const arcb200_state_t *d_states, const int64_t *d_offsets,
-                                  const double *d_psi, const double *d_r, double *d_out);
-
 /* The same integrals for whole BLOCKS of state pairs as tensor-core Gram matrices:
  * block g computes out[out_off + a*ncols + b] for a in rows[row0..row0+nrows),
  * b in cols[col0..col0+ncols) (state indices), power 1|2.  All states must share the x grid

@@ -132,38 +132,6 @@ def test_c2_full_table_gram_vs_per_pair():
     assert worst <= 1e-8, worst
 
 
-def test_radial_run_kernel_bit_identical_to_per_pair_kernel():
-    """arcb200_radial_integrals_runs (psi_a read once per run of <= 8 pairs) against the per-pair
-    kernel on a sorted table with ragged run lengths: same summation order -> bit-identical."""
-    import torch
-    import arc_b200
-    from arc_b200 import radial, _lib
-    atom = arc_b200.Rubidium()
-    sts = [(n, l, l + .5) for l in (0, 1, 2) for n in range(22, 62)]
-    recs = np.array([atom._state_record(*s) for s in sts])
-    rb = radial.RadialBatch(recs)
-    rng = np.random.default_rng(4)
-    pr = []
-    for a in range(len(sts)):
-        nb = int(rng.integers(0, 21))                     # runs of 0 .. 20 partners
-        for b in rng.choice(len(sts), size=nb, replace=False):
-            pr.append((a, int(b), int(rng.integers(1, 3))))
-    pairs = np.array(pr, dtype=np.int32)
-    pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0], pairs[:, 2]))]
-    got = rb.integrals(pairs)                              # run kernel (sorted, long runs)
-    lib = _lib.load()
-    dev = torch.device("cuda", rb.device)
-    d_pairs = torch.from_numpy(pairs).to(dev)
-    ref = torch.empty(len(pairs), dtype=torch.float64, device=dev)
-    _lib.check(lib.arcb200_radial_integrals(rb.device, _lib.stream_ptr(rb.device), len(pairs), _lib.ptr(d_pairs),
-                                            _lib.ptr(rb.d_states), _lib.ptr(rb.d_offsets), _lib.ptr(rb.d_psi),
-                                            _lib.ptr(rb.d_r), _lib.ptr(ref)), "per-pair kernel")
-    assert rb.kernel_launches == 2                          # Numerov + one run-kernel launch
-    assert np.array_equal(got, ref.cpu().numpy())
-    perm = rng.permutation(len(pairs))                     # unsorted list: per-pair path, same numbers
-    assert np.array_equal(rb.integrals(pairs[perm]), got[perm])
-
-
 # ------------------------------------------------------------------------------ NumerovBack
 def test_numerov_back_arbitrary_callable_matches_reference(gold_dir):
     """NumerovBack (alkali_atom_functions.py:3939-4063) with arbitrary Python callables: against
