@@ -27,6 +27,9 @@ static inline size_t eig_align(size_t x) { return (x + 31) & ~(size_t)31; }
 // Two-stage tridiagonalisation (dense -> band -> tridiagonal) for N >= 1024; smaller matrices
 // are latency bound either way and use the one-stage kernel.  ARCB200_TWO_STAGE=0/1 overrides.
 int eig_use_two_stage(int N);
+// Pair sweeps with k << N take the bisection + inverse iteration path (eig_stein.cu): no N x N
+// eigenvector matrices are needed then, and the slot keeps only N x k windows (compact layout).
+int eig_stein_usable(int N, int k);
 
 static inline EigLayout eig_layout(int N, int nvec)
 {
@@ -37,10 +40,18 @@ static inline EigLayout eig_layout(int N, int nvec)
     L.nvec = nvec;
     const size_t np = (size_t)L.Npad;
     size_t o = 0;
+    // compact: only nvec << N eigenvectors are ever formed (stein path).  Q1 = the N x nvec window
+    // (>= 128 columns: the look-ahead band-reduction variant parks three panels there), Q2 = the four
+    // LU planes of the inverse iteration, U = the iterate + pivot flags, later the row-major window of
+    // the back-transformation.  C5 (N = 10384): 1.8 GB per matrix instead of 4.3 GB, so 2.4 x as many
+    // matrices share the kernels that give a matrix one CTA (bulge chasing, panel QR, Q2).
+    const bool compact = nvec > 0 && nvec < N && eig_stein_usable(N, nvec);
+    const size_t kp = (size_t)((nvec + 31) & ~31), kq = kp < 128 ? 128 : kp;
     L.oA = o;      o += np * np;
-    L.oQ1 = o;     o += np * np;
-    L.oQ2 = o;     o += np * np;
-    L.oU = o;      o += np * (np + 64);             // also the row-major Z window of the Q2 pass
+    L.oQ1 = o;     o += compact ? np * kq : np * np;
+    L.oQ2 = o;     o += compact ? 4 * np * kp : np * np;
+    L.oU = o;      o += compact ? (np + 64) * (kq + 64) + np * kp / 8 + 64
+                                : np * (np + 64);   // also the row-major Z window of the Q2 pass
     L.oWp = o;     o += np * EIG_PB;
     L.oVp = o;     o += np * EIG_PB;
     L.oTrans = o;  o += (size_t)L.NB * np;
@@ -86,8 +97,7 @@ int eig_stedc(const EigSlots &S, int nmat, cudaStream_t st, int *launches, int s
               double sigma = 0.0, int32_t *d_sel0 = nullptr);
 // stage 2 for pair sweeps with k << N (eig_stein.cu): the k eigenpairs nearest sigma by bisection +
 // inverse iteration; eigenvalues land in oLam[0..k), eigenvectors of T in Q1 columns 0..k-1,
-// d_sel0[mat] = 0.  eig_stein_usable: k small enough for the work arrays (4 N k doubles in Q2).
-int eig_stein_usable(int N, int k);
+// d_sel0[mat] = 0.
 int eig_stein(const EigSlots &S, int nmat, int k, double sigma, int32_t *d_sel0, cudaStream_t st, int *launches);
 // stage 3: Z = Q_house * Q1[:, sel0 : sel0+nsel]  (in place on Q1 columns)
 int eig_ormtr(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, cudaStream_t st,

@@ -1505,10 +1505,19 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 {
     if (!S.L.two_stage) { arcb200_set_error("sy2sb: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
-    // one CTA per matrix needs about as many matrices as SMs; smaller batches (large N) spread
-    // every matrix over many CTAs with one launch per phase and panel
+    // One CTA per matrix is the faster kernel per matrix (1.05 ms against 1.15 ms at N = 2363) but only in
+    // whole waves of one matrix per SM; a batch that leaves more than ~8 % of its last wave idle goes to
+    // the per-phase kernels with many CTAs per matrix (measured, tools/ab_multi.py: 74 matrices 109 ms
+    // against 155 ms, 125: 151 / 156, 250: 286 / 311, 296: 338 / 312).
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int waves = (nmat + sms - 1) / sms;
     const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
-    const bool multi = em ? (em[0] == '1') : (nmat < 74);
+    const bool multi = em ? (em[0] == '1') : ((double)nmat < 0.92 * (double)(waves * sms));
     if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
     // Three kernels, measured on C3 (N = 2363, 296 matrices; profiles/r02_ab_sy2sb_variants_c3.json):
     //   lockstep (default)  312 ms   block barrier per tile step, per-thread cp.async

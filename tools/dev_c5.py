@@ -11,11 +11,12 @@ calc.defineBasis(np.pi / 4, 0, 3, 4, 10e9, Bz=1e-4)
 N = len(calc.basisStates)
 print("C5 defineBasis: %d channels, N=%d, matR nnz %d, %.1f s" % (len(calc.channel), N, calc.matR[0].nnz, time.time() - t0), flush=True)
 R = np.linspace(2, 20, nR)
-t0 = time.time()
-calc.diagonalise(R, k)
-torch.cuda.synchronize()
-dt = time.time() - t0
-print("diagonalise %d R points k=%d: %.2f s (%.2f s/point)" % (nR, k, dt, dt / nR), flush=True)
+for rep in range(2):           # the first call maps the workspace (~100 GB): time the second
+    t0 = time.time()
+    calc.diagonalise(R, k)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    print("diagonalise %d R points k=%d: %.2f s (%.3f s/point), %d launches" % (nR, k, dt, dt / nR, calc.last_sweep.kernel_launches), flush=True)
 # check one point against numpy on the host (dense eigh of the same matrix)
 i = 0
 H = calc.matDiagonal.toarray() + calc.matR[0].toarray() / (calc.r[i] * 1e-6) ** 3
