@@ -47,88 +47,75 @@ class StarkBasisGenerator:
     def _eFieldCoupling(self, n1, l1, j1, mj1, n2, l2, j2, mj2, eField, s=0.5):
         return self._eFieldCouplingDivE(n1, l1, j1, mj1, n2, l2, j2, mj2, s=s) * eField
 
+    # ---- photon-order selection rules (calculations_atom_single.py:3318-3394), as one table:
+    # a state |t> is reached from |s> with `order` photons of polarisation q when dl = |ls - lt|
+    # equals `order` with dj following dl (stretched), or -- with no change of l -- j flips at fixed l
+    # (order 1, j = l +- s on either side) / nothing changes but m_j (order 2)
+    @staticmethod
+    def _photonCoupling(order, ns, ls, js, mjs, nt, lt, jt, mjt, q, s=0.5):
+        if (ns, ls, js, mjs) == (nt, lt, jt, mjt):
+            return False
+        if (mjt - mjs) / order != q:
+            return False
+        dl, stretched = ls - lt, (ls - lt == js - jt)
+        if order == 1:
+            return abs(dl) == 1 and (stretched or (js == jt and (js == ls + s or jt == lt + s)))
+        return (abs(dl) == 2 and stretched) or (dl == 0 and js == jt)
+
     def _onePhotonCoupling(self, ns, ls, js, mjs, nt, lt, jt, mjt, q, s=0.5):
-        """calculations_atom_single.py:3318-3355."""
-        if (ns == nt) and (ls == lt) and (js == jt) and (mjs == mjt):
-            return False
-        elif (abs(ls - lt) == 1) and (mjt - mjs == q):
-            if ls - lt == js - jt:
-                return True
-            elif (js == jt) and ((js == ls + s) or (jt == lt + s)):
-                return True
-            return False
-        return False
+        return self._photonCoupling(1, ns, ls, js, mjs, nt, lt, jt, mjt, q, s)
 
     def _twoPhotonCoupling(self, ns, ls, js, mjs, nt, lt, jt, mjt, q, s=0.5):
-        """calculations_atom_single.py:3357-3394."""
-        if (ns == nt) and (ls == lt) and (js == jt) and (mjs == mjt):
-            return False
-        elif (abs(ls - lt) == 2) and (ls - lt == js - jt) and ((mjt - mjs) / 2 == q):
-            return True
-        elif ((ls - lt) == 0) and (js == jt) and ((mjt - mjs) / 2 == q):
-            return True
-        return False
+        return self._photonCoupling(2, ns, ls, js, mjs, nt, lt, jt, mjt, q, s)
 
     def defineBasis(self, n, l, j, mj, q=0, nMin=None, nMax=None, maxL=None, Bz=0, edN=0,
                     basisStates=None, progressOutput=False, debugOutput=False, s=0.5):
-        """calculations_atom_single.py:3396-3487."""
+        """Same call signature and attributes as calculations_atom_single.py:3396-3487: either an
+        explicit list of basis states, or the window (nMin, nMax, maxL) filtered by photon order edN."""
         self.n, self.l, self.j, self.mj, self.Bz, self.s = n, l, j, mj, Bz, s
+        target = [n, l, j, mj]
         if basisStates is not None:
-            self._defineBasisStates(basisStates)
-        elif nMin is not None and nMax is not None and maxL is not None:
-            self.q = q
-            if edN in [0, 1, 2]:
-                self.edN = edN
-            else:
-                raise ValueError("edN must be 0, 1, or 2")
-            self.nMin, self.nMax, self.maxL = nMin, nMax, maxL
-            self._findBasisStates(progressOutput, debugOutput)
+            if target not in basisStates:
+                raise ValueError(f"Target state {target} not in states list")
+            self.basisStates = basisStates
+            self.indexOfCoupledState = basisStates.index(target)
         else:
-            raise ValueError("Input arguments are not complete. "
-                             + "Either specify nMin, nMax, maxL or basisStates")
+            if None in (nMin, nMax, maxL):
+                raise ValueError("Input arguments are not complete. "
+                                 + "Either specify nMin, nMax, maxL or basisStates")
+            if edN not in (0, 1, 2):
+                raise ValueError("edN must be 0, 1, or 2")
+            self.q, self.edN = q, edN
+            self.nMin, self.nMax, self.maxL = nMin, nMax, maxL
+            self.basisStates = self._enumerateBasis()
+            # the reference appends the target where it meets it in the (n, l, j) scan
+            self.indexOfCoupledState = self.basisStates.index(target)
+            if progressOutput:
+                print("Found ", len(self.basisStates), " states.")
+        self.targetState = self.basisStates[self.indexOfCoupledState]
         self._buildHamiltonian(progressOutput, debugOutput)
 
-    def _defineBasisStates(self, states_list):
-        """calculations_atom_single.py:3489-3504."""
-        self.basisStates = states_list
-        t_state = [self.n, self.l, self.j, self.mj]
-        try:
-            self.indexOfCoupledState = states_list.index(t_state)
-        except ValueError:
-            raise ValueError(f"Target state {t_state} not in states list")
-        self.targetState = states_list[self.indexOfCoupledState]
+    def _admitted_mj(self, tn, tl, tj):
+        """m_j with which (tn, tl, tj) enters the basis, or None (calculations_atom_single.py:3529-3574:
+        the target itself; every state above the ground state for edN = 0; else the states one -- and,
+        for edN = 2, two -- photons of polarisation q away from the target)."""
+        n, l, j, mj, q, s = self.n, self.l, self.j, self.mj, self.q, self.s
+        if (tn, tl, tj) == (n, l, j):
+            return mj
+        if self.edN == 0:
+            # (`[tn, tl, tj] in extraLevels` is a list-in-list-of-tuples test in the reference: never true)
+            return mj + q if (tn >= self.atom.groundStateN or [tn, tl, tj] in self.atom.extraLevels) else None
+        if self._photonCoupling(1, n, l, j, mj, tn, tl, tj, mj + q, q, s):
+            return mj + q
+        if self.edN == 2 and self._photonCoupling(2, n, l, j, mj, tn, tl, tj, mj + 2 * q, q, s):
+            return mj + 2 * q
+        return None
 
-    def _findBasisStates(self, progressOutput=False, debugOutput=False):
-        """calculations_atom_single.py:3506-3582 (same enumeration order)."""
-        states = []
-        n, l, j, mj, q, s, edN = self.n, self.l, self.j, self.mj, self.q, self.s, self.edN
-        indexOfCoupledState = 0
-        index = 0
-        for tn in range(self.nMin, self.nMax + 1):
-            for tl in range(min(self.maxL + 1, tn)):
-                for tj in np.linspace(tl - s, tl + s, round(2 * s + 1)):
-                    if abs(mj + q) - 0.1 > tj:
-                        continue
-                    if (n == tn) and (l == tl) and (j == tj):
-                        states.append([tn, tl, tj, mj])
-                        indexOfCoupledState = index
-                    elif (edN == 0) and (tn >= self.atom.groundStateN
-                                         or [tn, tl, tj] in self.atom.extraLevels):
-                        states.append([tn, tl, tj, mj + q])
-                        index += 1
-                    elif (edN == 1 or edN == 2) and self._onePhotonCoupling(
-                            n, l, j, mj, tn, tl, tj, mj + q, q, s):
-                        states.append([tn, tl, tj, mj + q])
-                        index += 1
-                    elif edN == 2 and self._twoPhotonCoupling(
-                            n, l, j, mj, tn, tl, tj, mj + 2 * q, q, s):
-                        states.append([tn, tl, tj, mj + 2 * q])
-                        index += 1
-        if progressOutput:
-            print("Found ", len(states), " states.")
-        self.basisStates = states
-        self.indexOfCoupledState = indexOfCoupledState
-        self.targetState = states[indexOfCoupledState]
+    def _enumerateBasis(self):
+        s = self.s
+        scan = ((tn, tl, tj) for tn in range(self.nMin, self.nMax + 1) for tl in range(min(self.maxL + 1, tn))
+                for tj in np.linspace(tl - s, tl + s, round(2 * s + 1)) if not abs(self.mj + self.q) - 0.1 > tj)
+        return [[tn, tl, tj, m] for tn, tl, tj in scan for m in [self._admitted_mj(tn, tl, tj)] if m is not None]
 
     def _buildHamiltonian(self, progressOutput=False, debugOutput=False):
         """calculations_atom_single.py:3584-3668: `bareEnergies` (Hz) and `V` (Hz/(V/m),
