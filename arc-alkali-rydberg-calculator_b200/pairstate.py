@@ -706,6 +706,7 @@ class PairStateInteractions:
         trivial = wgd.trivial
         self.matR = []
         self._matR_coo = []
+        blkcache = {}
         for c in self.coupling:
             rows, cols, vals = [], [], []
             c = c.tocsr()
@@ -719,24 +720,32 @@ class PairStateInteractions:
                         continue
                     rho = c.data[p_]
                     chj = self.channel[jjc]
-                    af = self._angular_factors(chi[1], chi[2], chi[4], chi[5],
-                                               chj[1], chj[2], chj[4], chj[5])
-                    if af is None or af[0] == 0.0:
+                    # the angular block and its sparsity pattern depend on the eight (l, j) numbers
+                    # only (the m sub-levels kept per channel follow from j1, j2): built once per key
+                    akey = (chi[1], chi[2], chi[4], chi[5], chj[1], chj[2], chj[4], chj[5])
+                    hit = blkcache.get(akey)
+                    if hit is None:
+                        af = self._angular_factors(*akey)
+                        if af is None or af[0] == 0.0:
+                            hit = ()
+                        else:
+                            elem, terms = af
+                            if trivial:
+                                B = elem * sum(f * np.kron(A, Bm) for f, A, Bm in terms)
+                            else:
+                                D1, D2 = wgd.get(chi[2]), wgd.get(chi[5])
+                                D3, D4 = wgd.get(chj[2]), wgd.get(chj[5])
+                                B = elem * sum(f * np.kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
+                                               for f, A, Bm in terms)
+                                B = B.real
+                            blk = B[np.ix_(prod_idx[jjc], prod_idx[ii])]     # rows: j states, cols: i states
+                            jr, ic = np.nonzero(np.abs(blk) > 1.0e-5)
+                            hit = (jr, ic, blk[jr, ic]) if len(jr) else ()
+                        blkcache[akey] = hit
+                    if not hit:
                         continue
-                    elem, terms = af
-                    if trivial:
-                        B = elem * sum(f * np.kron(A, Bm) for f, A, Bm in terms)
-                    else:
-                        D1, D2 = wgd.get(chi[2]), wgd.get(chi[5])
-                        D3, D4 = wgd.get(chj[2]), wgd.get(chj[5])
-                        B = elem * sum(f * np.kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
-                                       for f, A, Bm in terms)
-                        B = B.real
-                    blk = B[np.ix_(prod_idx[jjc], prod_idx[ii])]     # rows: j states, cols: i states
-                    jr, ic = np.nonzero(np.abs(blk) > 1.0e-5)
-                    if len(jr) == 0:
-                        continue
-                    v = rho * blk[jr, ic]
+                    jr, ic, bv = hit
+                    v = rho * bv
                     gi = self.index[ii] + ic
                     gj = self.index[jjc] + jr
                     rows.append(gi); cols.append(gj); vals.append(v)
