@@ -62,6 +62,7 @@ _SIGNATURES = {
                                        c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "arcb200_dmma_peak": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "arcb200_dfma_peak": (c_int, [c_int, c_vp, c_vp, c_vp]),
+    "arcb200_tile_stream_probe": (c_int, [c_int, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_dbl, c_vp]),
     "arcb200_sy2sb_batched": (c_int, [c_int, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 

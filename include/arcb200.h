@@ -43,6 +43,15 @@ int arcb200_dmma_peak(int device, void *stream, double *d_scratch, double *h_tfl
 /* Same for the plain FP64 FMA pipe (DFMA), 16 independent chains per thread. */
 int arcb200_dfma_peak(int device, void *stream, double *d_scratch, double *h_tflops);
 
+/* Tile-stream probe (diagnostic): every warp of one 8-warp CTA per SM streams 32 x 32 FP64 tiles by
+ * cp.async, `depth` (1|2) tiles ahead, and spends 128 DMMAs on each -- the memory side of the band
+ * reduction's symmetric product in isolation.  mode 0: tiles of a column-major matrix (32 segments of
+ * 256 B, lda doubles apart), mode 1: tile-major (8 KB contiguous).  d_buf: >= sm_count * lda^2 doubles.
+ * h_out = {ms per launch, fraction of dmma_tflops, GB/s}. */
+int arcb200_tile_stream_probe(int device, void *stream, const double *d_buf, int64_t buf_doubles,
+                              int32_t lda, int32_t ntiles_per_warp, int32_t mode, int32_t depth,
+                              double dmma_tflops, double *h_out);
+
 /* ------------------------------------------------------------------------ */
 /* subsystem (1): Numerov radial wavefunctions + radial integrals            */
 /* ------------------------------------------------------------------------ */
