@@ -611,6 +611,285 @@ static __device__ __forceinline__ void s1_fused_pass(const S1Ctx &c, const S1Fz 
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------
+// barrier-free tensor phases: per-warp tile rings + a shared operand ring on mbarriers
+// ------------------------------------------------------------------------------------------
+// arcb200_tile_stream_probe (csrc/micro.cu): eight independent warps per SM, each streaming its own
+// tiles by cp.async one tile ahead and spending 128 DMMAs on each, run at 0.90 of the DMMA rate
+// (4.2 TB/s); ending every step like the lockstep kernel does -- wait for the next tile, block
+// barrier -- drops that to 0.75: a step then takes the slowest of eight tile latencies.  Here no warp
+// ever waits for another warp's tile.  The only shared data of a step, the operand tile(s) V_q (or
+// W_J, V_J), goes through a four-stage ring: every warp copies its four rows of the operand two steps
+// ahead (cp.async, completion counted on the stage's `full` mbarrier, 256 arrivals) and releases a
+// stage through its `empty` mbarrier (8 arrivals), so the warps may drift two steps apart.  Tile
+// prefetch runs across row-group boundaries.  All warps walk the same (group, step) schedule.
+struct S1Ring {
+    double(*ring)[2][32][BSTR];    // [stage][op][row][col]
+    unsigned long long *full, *empty;   // [4] each
+};
+
+static __device__ __forceinline__ void s1_symm_ring(const S1Ctx &c, const S1Ring &r, int p, unsigned &gu)
+{
+    constexpr int TSTR = S1_TSTR;
+    const int lane = c.lane, grp = c.grp, tig = c.tig, wid = c.wid, np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *Tw = c.Tw;
+    const int Jt = p + 1, m = NB - (p + 1);
+    const int ng = (m + 7) >> 3;
+    const int S = ng * m;                       // steps of the phase: step u <-> (group u / m, q = Jt + u % m)
+    const unsigned gu0 = gu;
+    __syncthreads();
+    auto fill = [&](int u) {                    // my four rows of V_q of step u (commits one cp.async group)
+        if (u < S) {
+            const unsigned g = gu0 + (unsigned)u;
+            const int st = g & 3;
+            if (g >= 4) mbar_wait(&r.empty[st], ((g >> 2) - 1) & 1u);
+            const int q = Jt + u % m;
+            const int row = 4 * wid + (lane >> 4), cc = (lane & 15) * 2;
+            cp_async16_t(&r.ring[st][0][row][cc], Vp + (size_t)row * np + 32 * q + cc);
+            cp_async16_t(&r.ring[st][0][row + 2][cc], Vp + (size_t)(row + 2) * np + 32 * q + cc);
+            cp_async_mbar_arrive(&r.full[st]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    auto tile = [&](int u) {                    // my tile of step u into buffer u & 1 (commits one group)
+        if (u < S) {
+            const int i = Jt + 8 * (u / m) + wid, q = Jt + u % m;
+            if (i < NB) {
+                const int Ib = max(i, q), Jb = min(i, q);
+                // four running source pointers: a cp.async holds its address registers until the LSU has
+                // read them (17 cycles), so one pointer bumped 16 times serialises the 16 copies (640 cycles)
+                const size_t sstep = 2 * (size_t)lda;
+                const double *s0 = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
+                const double *s1 = s0 + sstep, *s2 = s1 + sstep, *s3 = s2 + sstep;
+                double *dst = Tw + (u & 1) * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    cp_async16_t(dst + (8 * k) * TSTR, s0);
+                    cp_async16_t(dst + (8 * k + 2) * TSTR, s1);
+                    cp_async16_t(dst + (8 * k + 4) * TSTR, s2);
+                    cp_async16_t(dst + (8 * k + 6) * TSTR, s3);
+                    s0 += 4 * sstep; s1 += 4 * sstep; s2 += 4 * sstep; s3 += 4 * sstep;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    fill(0);
+    fill(1);
+    tile(0);
+    double acc[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    for (int u = 0; u < S; ++u) {
+        fill(u + 2);
+        tile(u + 1);
+        asm volatile("cp.async.wait_group 2;\n" ::: "memory");      // my tile of step u has landed
+        __syncwarp();
+        const unsigned g = gu0 + (unsigned)u;
+        const int st = g & 3;
+        mbar_wait(&r.full[st], (g >> 2) & 1u);
+        const int i = Jt + 8 * (u / m) + wid, q = Jt + u % m;
+        if (i < NB) {
+            const double *tw = Tw + (u & 1) * (32 * TSTR);
+            if (q <= i) {
+                const double *pd = tw + tig * TSTR + grp;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double fa[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double b = r.ring[st][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                    }
+                }
+            } else {
+                const double *pt = tw + grp * TSTR + tig;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double fa[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double b = r.ring[st][0][8 * y + grp][4 * ks + tig];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
+                    }
+                }
+            }
+            if (q == NB - 1) {                  // last step of the row: X_i
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            Wp[(size_t)(8 * y + 2 * tig + h) * np + 32 * i + 8 * x + grp] = acc[x][y][h];
+                            acc[x][y][h] = 0.0;
+                        }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.empty[st]);
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    gu = gu0 + (unsigned)S;
+    __syncthreads();
+}
+
+static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Ring &r, int p, unsigned &gu)
+{
+    constexpr int TSTR = S1_TSTR;
+    const int lane = c.lane, grp = c.grp, tig = c.tig, wid = c.wid, np = c.np, lda = c.lda, NB = c.NB;
+    double *A = c.A;
+    double *__restrict__ Wp = c.Wp;
+    double *__restrict__ Vp = c.Vp;
+    double *Tw = c.Tw;
+    double *Tv = Tw + 32 * TSTR;
+    const int Jt = p + 1, m = NB - (p + 1);
+    const int ng = (m + 7) >> 3;
+    const unsigned gu0 = gu;
+    // group t: block rows Jt + 8 t + wid, steps J = Jt .. min(Jt + 8 t + 7, NB - 1)
+    auto group_last = [&](int t) { return min(Jt + 8 * t + 7, NB - 1); };
+    __syncthreads();
+    int ft = 0, fJ = Jt;                        // schedule position of the next operand fill
+    unsigned fg = gu0;
+    auto fill = [&]() {                         // my four rows of W_J and V_J (one cp.async group)
+        if (ft < ng) {
+            const int st = fg & 3;
+            if (fg >= 4) mbar_wait(&r.empty[st], ((fg >> 2) - 1) & 1u);
+            const int row = 4 * wid + (lane >> 4), cc = (lane & 15) * 2;
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2) {
+                const int k = row + 2 * t2;
+                cp_async16_t(&r.ring[st][0][k][cc], Wp + (size_t)k * np + 32 * fJ + cc);
+                cp_async16_t(&r.ring[st][1][k][cc], Vp + (size_t)k * np + 32 * fJ + cc);
+            }
+            cp_async_mbar_arrive(&r.full[st]);
+            ++fg;
+            if (++fJ > group_last(ft)) { ++ft; fJ = Jt; }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    auto tile_to = [&](double *dst0, const double *src0, size_t pitch) {
+        const size_t sstep = 2 * pitch;
+        const double *s0 = src0 + (size_t)(lane >> 4) * pitch + (lane & 15) * 2;
+        const double *s1 = s0 + sstep, *s2 = s1 + sstep, *s3 = s2 + sstep;
+        double *dst = dst0 + (lane >> 4) * TSTR + (lane & 15) * 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cp_async16_t(dst + (8 * k) * TSTR, s0);
+            cp_async16_t(dst + (8 * k + 2) * TSTR, s1);
+            cp_async16_t(dst + (8 * k + 4) * TSTR, s2);
+            cp_async16_t(dst + (8 * k + 6) * TSTR, s3);
+            s0 += 4 * sstep; s1 += 4 * sstep; s2 += 4 * sstep; s3 += 4 * sstep;
+        }
+    };
+    fill();
+    fill();
+    unsigned g = gu0;
+    const double *tv = Tv + tig * TSTR + 4 * grp;
+    const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
+    for (int t = 0; t < ng; ++t) {
+        const int I = Jt + 8 * t + wid;
+        const bool act = I < NB;
+        const int Jlast = group_last(t);
+        double fw[4][8];
+        if (act) {
+            // row operands: -W_I to registers, -V_I to the second tile; the first C tile (unless the
+            // previous group already prefetched it)
+            tile_to(Tv, Vp + 32 * I, np);
+            if (t == 0) tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * I, lda);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
+                const double2 w0 = pw2[0], w1 = pw2[1];
+                fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
+            }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        if (act) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) Tv[lane * TSTR + rr] = -Tv[lane * TSTR + rr];
+        }
+        __syncwarp();
+        for (int J = Jt; J <= Jlast; ++J, ++g) {
+            const int st = g & 3;
+            const bool work = act && J <= I;
+            fill();                                                    // operands two steps ahead
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");    // everything but that fill: my C tile
+            __syncwarp();
+            double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
+            if (work) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
+                    const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
+                    const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                    c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
+                    c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
+                }
+                // the tile buffer is refilled below: its loads have to have landed
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    asm volatile("" ::"d"(c0[0][y]), "d"(c0[1][y]), "d"(c0[2][y]), "d"(c0[3][y]), "d"(c1[0][y]), "d"(c1[1][y]),
+                                 "d"(c1[2][y]), "d"(c1[3][y]));
+            }
+            __syncwarp();
+            // next C tile of this row, or -- on its last step -- the first one of my row in the next group
+            if (act && J + 1 <= I) {
+                tile_to(Tw, A + (size_t)(32 * (J + 1)) * lda + 32 * I, lda);
+            } else if (J == min(I, Jlast) && t + 1 < ng && I + 8 < NB) {
+                tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * (I + 8), lda);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            mbar_wait(&r.full[st], (g >> 2) & 1u);
+            if (work) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
+                    const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
+                    const double fv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double bw = r.ring[st][0][4 * ks + tig][8 * y + grp];
+                        const double bv = r.ring[st][1][4 * ks + tig][8 * y + grp];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
+                        }
+                    }
+                }
+                double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
+                    double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
+                    o0[0] = make_double2(c0[0][y], c0[1][y]);
+                    o0[1] = make_double2(c0[2][y], c0[3][y]);
+                    o1[0] = make_double2(c1[0][y], c1[1][y]);
+                    o1[1] = make_double2(c1[2][y], c1[3][y]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r.empty[st]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    gu = g;
+    __syncthreads();
+}
+
 static __device__ __forceinline__ void s1_band_copy(const TsArgs &a, double *slot, double *A, int lda, int tid, int NT)
 {
     const int np = a.Npad;
@@ -1479,6 +1758,68 @@ __global__ void __launch_bounds__(256, 1) sy2sb_fused_kernel(TsArgs a)
 }
 
 
+// Barrier-free tensor phases (see s1_symm_ring): same algorithm and phase order as the lockstep kernel.
+constexpr size_t S1RING_SMEM_BYTES = (size_t)(2 * 8 * 32 * S1_TSTR + 2 * 4608 + 128) * sizeof(double) + 256;
+__global__ void __launch_bounds__(256, 1) sy2sb_ring_kernel(TsArgs a)
+{
+    constexpr int WARPS = 8;
+    constexpr int TSTR = S1_TSTR;
+    constexpr int TILES = 2 * WARPS * 32 * TSTR;
+    const int mat = blockIdx.x;
+    double *slot = a.base + (size_t)mat * a.slot;
+    extern __shared__ double sm[];
+    S1Ctx c;
+    c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
+    c.np = a.Npad; c.lda = a.Npad; c.NB = a.NB;
+    c.A = slot + a.oA; c.Wp = slot + a.oWp; c.Vp = slot + a.oVp; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
+    // [transit tiles][operand ring: 4 stages x 2 tiles][small arrays][barriers]; the W phase uses the first two
+    // ring tiles as its operand tiles, T / G / M1 live in the second half of the ring (idle outside the tensor
+    // phases; T is reloaded from global memory after the symmetric product has used the ring)
+    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+    double *half2 = sm + TILES + 4608;
+    c.Ts = reinterpret_cast<double(*)[33]>(half2);
+    c.G = reinterpret_cast<double(*)[33]>(half2 + 1056);
+    c.M1 = reinterpret_cast<double(*)[33]>(half2 + 2 * 1056);
+    double *small = sm + TILES + 2 * 4608;
+    c.wv = reinterpret_cast<double(*)[32]>(small);
+    c.sred = reinterpret_cast<double(*)[16]>(small + 64);
+    c.taus = small + 96;
+    c.Tw = sm + c.wid * (2 * 32 * TSTR);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(small + 128);
+    S1Ring r;
+    r.ring = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+    r.full = bars;
+    r.empty = bars + 4;
+    if (c.tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&r.full[i], 256); mbar_init(&r.empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    unsigned gu = 0;               // operand-ring steps so far (stage = gu & 3, use = gu >> 2)
+    TSP_DECL
+    for (int p = 0; p < a.NB - 1; ++p) {
+        TSP(0)
+        s1_panel_qr<WARPS>(c, p);
+        TSP(1)
+        s1_tfactor<WARPS>(c, p);
+        TSP(2)
+        s1_symm_ring(c, r, p, gu);
+        TSP(3)
+        for (int t = c.tid; t < 1024; t += WARPS * 32) c.Ts[t >> 5][t & 31] = c.Tfac[(size_t)p * 1024 + t];
+        s1_wphase<WARPS>(c, p);
+        TSP(4)
+        s1_syr2k_ring(c, r, p, gu);
+        TSP(5)
+    }
+#ifdef TS_PROFILE
+    if (mat == 0 && c.tid == 0)
+        printf("sy2sb ring prof (10 kcycles): qr %lld tfac %lld symm %lld w %lld syr2k %lld\n", tsp_t[1] / 10000,
+               tsp_t[2] / 10000, tsp_t[3] / 10000, tsp_t[4] / 10000, tsp_t[5] / 10000);
+#endif
+    __syncthreads();
+    s1_band_copy(a, slot, c.A, c.lda, c.tid, WARPS * 32);
+}
+
 TsArgs make_args(const EigSlots &S)
 {
     const EigLayout &L = S.L;
@@ -1519,19 +1860,25 @@ int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
     const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
     const bool multi = em ? (em[0] == '1') : ((double)nmat < 0.92 * (double)(waves * sms));
     if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
-    // Three kernels, measured on C3 (N = 2363, 296 matrices; profiles/r02_ab_sy2sb_variants_c3.json):
-    //   lockstep (default)  312 ms   block barrier per tile step, per-thread cp.async
-    //   wg                  320 ms   decoupled warpgroups, TMA-unit bulk copies + mbarriers
-    //                       (309 ms with per-thread cp.async tracked by the same mbarriers: the decoupling is
-    //                       worth 1 %, the ELECT / R2UR serialisation of one UBLKCP per tile column costs 3.5 %)
-    //   fused               392 ms   look-ahead: rank-2k update fused with the next symmetric product
-    // ARCB200_SY2SB_VARIANT = lockstep | wg | fused selects one.
+    // Four kernels for whole waves of one matrix per SM, measured on C3 (N = 2363, 296 matrices;
+    // profiles/r02_ab_sy2sb_variants_c3.json):
+    //   ring (default)      barrier-free tensor phases: per-warp tile rings + shared operand ring on mbarriers
+    //   lockstep            block barrier per tile step, per-thread cp.async (round 1)
+    //   wg                  decoupled warpgroups, TMA-unit bulk copies + mbarriers
+    //   fused               look-ahead: rank-2k update fused with the next symmetric product
+    // ARCB200_SY2SB_VARIANT = ring | lockstep | wg | fused selects one.
     const char *evv = getenv("ARCB200_SY2SB_VARIANT");
     const bool wgonly = evv && evv[0] == 'w';
     const bool fusedk = evv && evv[0] == 'f';
+    const bool lockk = evv && evv[0] == 'l';
+    const bool ringk = !wgonly && !fusedk && !lockk;
     const char *ev = getenv("ARCB200_SY2SB_WARPS");      // tuning knob (lockstep kernel only)
     const int warps = ev ? atoi(ev) : 8;
-    if (fusedk) {
+    if (ringk) {
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)S1RING_SMEM_BYTES));
+        sy2sb_ring_kernel<<<nmat, 256, S1RING_SMEM_BYTES, st>>>(a);
+    } else if (fusedk) {
         ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)S1FZ_SMEM_BYTES));
         sy2sb_fused_kernel<<<nmat, 256, S1FZ_SMEM_BYTES, st>>>(a);

@@ -45,8 +45,9 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 // Tile-stream probe: the memory side of the band reduction's symmetric product in isolation.  One CTA of
 // eight warps per SM and matrix; every warp streams 32 x 32 FP64 tiles of its matrix into a shared-memory
 // ring by cp.async (DEPTH tiles ahead) and spends 128 DMMAs on each (the tile's fragments are the A
-// operand, so the data is really consumed).  mode 0: column-major matrix, a tile is 32 segments of 256 B
-// `lda` doubles apart (the layout of the sweep workspace); mode 1: tile-major, a tile is 8 KB contiguous.
+// operand, so the data is really consumed).  mode bit 1 (value 2): end every step like the lockstep
+// kernel does (wait for the next tile, block barrier).  mode bit 0 = 0: column-major matrix, a tile is 32 segments of 256 B
+// `lda` doubles apart (the layout of the sweep workspace); bit 0 = 1: tile-major, a tile is 8 KB contiguous.
 // Reports the time per tile against the pure DMMA time.
 template <int DEPTH>
 __global__ void __launch_bounds__(256, 1) tile_probe_kernel(const double *base, size_t mat_stride, int lda, int ntiles,
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256, 1) tile_probe_kernel(const double *base, 
             const int idx = t * 8 + wid;
             const double *src;
             size_t step;
-            if (mode == 0) {
+            if ((mode & 1) == 0) {
                 const int I = idx % NBr, J = (idx / NBr) % NBr;
                 src = A + (size_t)(32 * J + (lane >> 4)) * lda + 32 * I + (lane & 15) * 2;
                 step = 2 * (size_t)lda;
@@ -109,6 +110,10 @@ __global__ void __launch_bounds__(256, 1) tile_probe_kernel(const double *base, 
             }
         }
         __syncwarp();
+        if (mode & 2) {            // the band-reduction kernel's step end: next tile landed, block barrier
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
+        }
     }
     double s = 0.0;
 #pragma unroll

@@ -129,12 +129,13 @@ class StarkMap:
 
         mat1 = np.zeros((dimension, dimension), dtype=np.double)
         mat2 = np.zeros((dimension, dimension), dtype=np.double)
+        zeeman = {}                                   # depends on (l, j, mj) only
         for ii in range(dimension):
+            kz = (states[ii][1], states[ii][2], states[ii][3])
+            if kz not in zeeman:
+                zeeman[kz] = self.atom.getZeemanEnergyShift(kz[0], kz[1], kz[2], self.Bz, s=self.s) / C_h * 1.0e-9
             mat1[ii][ii] = (self.atom.getEnergy(states[ii][0], states[ii][1], states[ii][2],
-                                                s=self.s) * C_e / C_h * 1e-9
-                            + self.atom.getZeemanEnergyShift(states[ii][1], states[ii][2],
-                                                             states[ii][3], self.Bz, s=self.s)
-                            / C_h * 1.0e-9)
+                                                s=self.s) * C_e / C_h * 1e-9 + zeeman[kz])
         ang = {}
         for a, b in pairs:
             ii, jj = (a, b) if a < b else (b, a)

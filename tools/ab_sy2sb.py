@@ -28,8 +28,8 @@ wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N))
 work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
 out = {"N": N, "batch": nb}
 bands = {}
-for variant in ("lockstep", "wg", "fused"):
-    os.environ["ARCB200_SY2SB_VARIANT"] = variant      # "fused" (= anything else) is the default kernel
+for variant in ("lockstep", "wg", "fused", "ring"):
+    os.environ["ARCB200_SY2SB_VARIANT"] = variant
     band = torch.zeros((nb, N, 33), dtype=torch.float64, device=dev)
 
     def run():
@@ -69,11 +69,13 @@ def band_eigs(bb):
 worst = 0.0
 for m in range(min(nb, 3)):
     wr = np.linalg.eigvalsh(A[m])
-    for v in ("wg", "fused"):
+    for v in ("wg", "fused", "ring"):
         worst = max(worst, float(np.abs(band_eigs(bands[v][m]) - wr).max() / np.abs(wr).max()))
 out["eig_err_worst_of_3_matrices_wg_fused"] = worst
 out["band_maxdiff_wg_vs_lockstep"] = float(np.abs(bands["wg"] - bands["lockstep"]).max())
 out["band_maxdiff_fused_vs_lockstep"] = float(np.abs(bands["fused"] - bands["lockstep"]).max())
 out["speedup_wg"] = out["lockstep"]["ms"] / out["wg"]["ms"]
 out["speedup_fused"] = out["lockstep"]["ms"] / out["fused"]["ms"]
+out["speedup_ring"] = out["lockstep"]["ms"] / out["ring"]["ms"]
+out["band_maxdiff_ring_vs_lockstep"] = float(np.abs(bands["ring"] - bands["lockstep"]).max())
 print(json.dumps(out))

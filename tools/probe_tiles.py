@@ -13,7 +13,7 @@ tf = ctypes.c_double(0.0)
 _lib.check(lib.arcb200_dmma_peak(0, _lib.stream_ptr(0), _lib.ptr(scratch), ctypes.addressof(tf)), "peak")
 out = {"dmma_tflops": tf.value, "lda": lda}
 h = (ctypes.c_double * 3)()
-for mode, name in ((0, "column_major_256B_segments"), (1, "tile_major_8KB")):
+for mode, name in ((0, "column_major_256B_segments"), (1, "tile_major_8KB"), (2, "column_major_block_barrier_per_step")):
     for depth in (1, 2):
         _lib.check(lib.arcb200_tile_stream_probe(0, _lib.stream_ptr(0), _lib.ptr(buf), buf.numel(), lda, 600, mode, depth,
                                                  tf.value, ctypes.addressof(h)), "probe")
