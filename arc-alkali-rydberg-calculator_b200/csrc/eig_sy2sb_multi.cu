@@ -18,8 +18,9 @@ using namespace ts;
 template <int WARPS, int PHASE>
 __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, int p)
 {
+    static_assert(WARPS == 8, "the operand ring is laid out for eight warps");
     constexpr int TSTR = S1_TSTR;
-    constexpr int UNI = 2 * WARPS * 32 * TSTR + 4608;   // 2 transit tiles per warp + operand tiles (doubles)
+    constexpr int TILES = 2 * WARPS * 32 * TSTR;
     const int mat = blockIdx.y;
     double *slot = a.base + (size_t)mat * a.slot;
     extern __shared__ double sm[];
@@ -27,26 +28,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, in
     c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
     c.np = a.Npad; c.lda = a.Npad; c.NB = a.NB;
     c.A = slot + a.oA; c.Wp = slot + a.oWp; c.Vp = slot + a.oVp; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
-    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + 2 * WARPS * 32 * TSTR);
-    c.Ts = reinterpret_cast<double(*)[33]>(sm + UNI);
-    c.G = reinterpret_cast<double(*)[33]>(sm + UNI + 1056);
-    c.M1 = reinterpret_cast<double(*)[33]>(sm + UNI + 2 * 1056);
-    c.wv = reinterpret_cast<double(*)[32]>(sm + UNI + 3 * 1056);
-    c.sred = reinterpret_cast<double(*)[16]>(sm + UNI + 3 * 1056 + 64);
-    c.taus = sm + UNI + 3 * 1056 + 96;
+    // shared-memory carve of sy2sb_ring_kernel: [transit tiles][operand ring / W-phase operand tiles | T, G, M1][small][barriers]
+    c.Bs = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+    double *half2 = sm + TILES + 4608;
+    c.Ts = reinterpret_cast<double(*)[33]>(half2);
+    c.G = reinterpret_cast<double(*)[33]>(half2 + 1056);
+    c.M1 = reinterpret_cast<double(*)[33]>(half2 + 2 * 1056);
+    double *small = sm + TILES + 2 * 4608;
+    c.wv = reinterpret_cast<double(*)[32]>(small);
+    c.sred = reinterpret_cast<double(*)[16]>(small + 64);
+    c.taus = small + 96;
     c.Tw = sm + c.wid * (2 * 32 * TSTR);
-    constexpr int ONE_GROUP = 1 << 20;               // group stride: this CTA takes exactly one row group
     if (PHASE == 0) {
         s1_panel_qr<WARPS>(c, p);
         s1_tfactor<WARPS>(c, p);
-    } else if (PHASE == 1) {
-        s1_symm_lockstep<WARPS>(c, p, (int)blockIdx.x, ONE_GROUP);
     } else if (PHASE == 2) {
         // the T factor of this panel comes back from global memory (phase 0 ran in another launch)
         for (int t = c.tid; t < 1024; t += WARPS * 32) c.Ts[t >> 5][t & 31] = c.Tfac[(size_t)p * 1024 + t];
         s1_wphase<WARPS>(c, p);
     } else {
-        s1_syr2k_lockstep<WARPS>(c, p, (int)blockIdx.x, ONE_GROUP);
+        // tensor phases: this CTA's row group, barrier-free (per-warp tile rings + shared operand ring)
+        unsigned long long *bars = reinterpret_cast<unsigned long long *>(small + 128);
+        S1Ring r;
+        r.ring = reinterpret_cast<double(*)[2][32][BSTR]>(sm + TILES);
+        r.full = bars;
+        r.empty = bars + 4;
+        if (c.tid == 0) {
+            for (int i = 0; i < 4; ++i) { mbar_init(&r.full[i], 256); mbar_init(&r.empty[i], 8); }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        unsigned gu = 0;
+        if (PHASE == 1) s1_symm_ring(c, r, p, gu, (int)blockIdx.x, 1);
+        else s1_syr2k_ring(c, r, p, gu, (int)blockIdx.x, 1);
     }
 }
 
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(256) band_extract_kernel(TsArgs a)
 int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launches)
 {
     constexpr int W = 8;
-    const size_t smem = (2 * W * 32 * 36 + 4608 + 3 * 1056 + 128) * sizeof(double);
+    const size_t smem = (size_t)(2 * W * 32 * 36 + 2 * 4608 + 128) * sizeof(double) + 256;
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

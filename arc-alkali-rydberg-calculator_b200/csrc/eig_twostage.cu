@@ -50,44 +50,6 @@ using namespace ts;
 // instead of eight.  All tile movement of these phases goes through the TMA unit: one
 // cp.async.bulk per lane moves a 256-byte tile column (SASS UBLKCP), completion is tracked by
 // mbarriers (SYNCS) -- no per-thread cp.async address loops, no cp.async.wait_group.
-static __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-static __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-static __device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-static __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// one bulk copy (TMA unit): `bytes` contiguous bytes global -> shared, completion counted on `bar`
-static __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-static __device__ __forceinline__ void cp_async_mbar_arrive(void *bar)
-{
-    // the barrier tracks the completion of this thread's earlier cp.async copies (SASS ARRIVES.LDGSTSBAR)
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-static __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-// all state spaces: generic-proxy writes to GLOBAL memory (panels, tiles) before bulk copies read them
-static __device__ __forceinline__ void fence_async_proxy_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-static __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory"); }
-
 struct S1Wg {                      // warpgroup-private state of the decoupled phases
     double(*Bs)[2][32][BSTR];      // this warpgroup's operand tiles [buf][op][row][col]
     unsigned long long *tbar;      // this warp's two tile barriers
@@ -341,10 +303,6 @@ static __device__ __forceinline__ void s1_syr2k_wg(const S1Ctx &c, const S1Wg &g
 // per 16 cycles) own one block row each -- -W_I in registers, -V_I, V'_I and a two-tile C ring in shared
 // memory; a producer warp streams the shared operands W_J, V_J, V'_J through a two-stage ring guarded
 // by full / empty mbarriers, so the compute warps never meet at a block barrier inside the pass.
-static __device__ __forceinline__ void mbar_arrive(void *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
 
 
 // Work split of the fused pass: compute warp w (0..3, one per scheduler) does nothing but wait for
@@ -608,285 +566,6 @@ static __device__ __forceinline__ void s1_fused_pass(const S1Ctx &c, const S1Fz 
         }
     }
     __threadfence();               // tile stores and reductions are performed before the block reads them
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
-// barrier-free tensor phases: per-warp tile rings + a shared operand ring on mbarriers
-// ------------------------------------------------------------------------------------------
-// arcb200_tile_stream_probe (csrc/micro.cu): eight independent warps per SM, each streaming its own
-// tiles by cp.async one tile ahead and spending 128 DMMAs on each, run at 0.90 of the DMMA rate
-// (4.2 TB/s); ending every step like the lockstep kernel does -- wait for the next tile, block
-// barrier -- drops that to 0.75: a step then takes the slowest of eight tile latencies.  Here no warp
-// ever waits for another warp's tile.  The only shared data of a step, the operand tile(s) V_q (or
-// W_J, V_J), goes through a four-stage ring: every warp copies its four rows of the operand two steps
-// ahead (cp.async, completion counted on the stage's `full` mbarrier, 256 arrivals) and releases a
-// stage through its `empty` mbarrier (8 arrivals), so the warps may drift two steps apart.  Tile
-// prefetch runs across row-group boundaries.  All warps walk the same (group, step) schedule.
-struct S1Ring {
-    double(*ring)[2][32][BSTR];    // [stage][op][row][col]
-    unsigned long long *full, *empty;   // [4] each
-};
-
-static __device__ __forceinline__ void s1_symm_ring(const S1Ctx &c, const S1Ring &r, int p, unsigned &gu)
-{
-    constexpr int TSTR = S1_TSTR;
-    const int lane = c.lane, grp = c.grp, tig = c.tig, wid = c.wid, np = c.np, lda = c.lda, NB = c.NB;
-    double *A = c.A;
-    double *__restrict__ Wp = c.Wp;
-    double *__restrict__ Vp = c.Vp;
-    double *Tw = c.Tw;
-    const int Jt = p + 1, m = NB - (p + 1);
-    const int ng = (m + 7) >> 3;
-    const int S = ng * m;                       // steps of the phase: step u <-> (group u / m, q = Jt + u % m)
-    const unsigned gu0 = gu;
-    __syncthreads();
-    auto fill = [&](int u) {                    // my four rows of V_q of step u (commits one cp.async group)
-        if (u < S) {
-            const unsigned g = gu0 + (unsigned)u;
-            const int st = g & 3;
-            if (g >= 4) mbar_wait(&r.empty[st], ((g >> 2) - 1) & 1u);
-            const int q = Jt + u % m;
-            const int row = 4 * wid + (lane >> 4), cc = (lane & 15) * 2;
-            cp_async16_t(&r.ring[st][0][row][cc], Vp + (size_t)row * np + 32 * q + cc);
-            cp_async16_t(&r.ring[st][0][row + 2][cc], Vp + (size_t)(row + 2) * np + 32 * q + cc);
-            cp_async_mbar_arrive(&r.full[st]);
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    auto tile = [&](int u) {                    // my tile of step u into buffer u & 1 (commits one group)
-        if (u < S) {
-            const int i = Jt + 8 * (u / m) + wid, q = Jt + u % m;
-            if (i < NB) {
-                const int Ib = max(i, q), Jb = min(i, q);
-                // four running source pointers: a cp.async holds its address registers until the LSU has
-                // read them (17 cycles), so one pointer bumped 16 times serialises the 16 copies (640 cycles)
-                const size_t sstep = 2 * (size_t)lda;
-                const double *s0 = A + (size_t)(32 * Jb + (lane >> 4)) * lda + 32 * Ib + (lane & 15) * 2;
-                const double *s1 = s0 + sstep, *s2 = s1 + sstep, *s3 = s2 + sstep;
-                double *dst = Tw + (u & 1) * (32 * TSTR) + (lane >> 4) * TSTR + (lane & 15) * 2;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    cp_async16_t(dst + (8 * k) * TSTR, s0);
-                    cp_async16_t(dst + (8 * k + 2) * TSTR, s1);
-                    cp_async16_t(dst + (8 * k + 4) * TSTR, s2);
-                    cp_async16_t(dst + (8 * k + 6) * TSTR, s3);
-                    s0 += 4 * sstep; s1 += 4 * sstep; s2 += 4 * sstep; s3 += 4 * sstep;
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    fill(0);
-    fill(1);
-    tile(0);
-    double acc[4][4][2];
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-    for (int u = 0; u < S; ++u) {
-        fill(u + 2);
-        tile(u + 1);
-        asm volatile("cp.async.wait_group 2;\n" ::: "memory");      // my tile of step u has landed
-        __syncwarp();
-        const unsigned g = gu0 + (unsigned)u;
-        const int st = g & 3;
-        mbar_wait(&r.full[st], (g >> 2) & 1u);
-        const int i = Jt + 8 * (u / m) + wid, q = Jt + u % m;
-        if (i < NB) {
-            const double *tw = Tw + (u & 1) * (32 * TSTR);
-            if (q <= i) {
-                const double *pd = tw + tig * TSTR + grp;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    double fa[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) fa[x] = pd[4 * ks * TSTR + 8 * x];
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const double b = r.ring[st][0][8 * y + grp][4 * ks + tig];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
-                    }
-                }
-            } else {
-                const double *pt = tw + grp * TSTR + tig;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    double fa[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) fa[x] = pt[8 * x * TSTR + 4 * ks];
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const double b = r.ring[st][0][8 * y + grp][4 * ks + tig];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) dmma_t(acc[x][y][0], acc[x][y][1], fa[x], b);
-                    }
-                }
-            }
-            if (q == NB - 1) {                  // last step of the row: X_i
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            Wp[(size_t)(8 * y + 2 * tig + h) * np + 32 * i + 8 * x + grp] = acc[x][y][h];
-                            acc[x][y][h] = 0.0;
-                        }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&r.empty[st]);
-    }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    gu = gu0 + (unsigned)S;
-    __syncthreads();
-}
-
-static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Ring &r, int p, unsigned &gu)
-{
-    constexpr int TSTR = S1_TSTR;
-    const int lane = c.lane, grp = c.grp, tig = c.tig, wid = c.wid, np = c.np, lda = c.lda, NB = c.NB;
-    double *A = c.A;
-    double *__restrict__ Wp = c.Wp;
-    double *__restrict__ Vp = c.Vp;
-    double *Tw = c.Tw;
-    double *Tv = Tw + 32 * TSTR;
-    const int Jt = p + 1, m = NB - (p + 1);
-    const int ng = (m + 7) >> 3;
-    const unsigned gu0 = gu;
-    // group t: block rows Jt + 8 t + wid, steps J = Jt .. min(Jt + 8 t + 7, NB - 1)
-    auto group_last = [&](int t) { return min(Jt + 8 * t + 7, NB - 1); };
-    __syncthreads();
-    int ft = 0, fJ = Jt;                        // schedule position of the next operand fill
-    unsigned fg = gu0;
-    auto fill = [&]() {                         // my four rows of W_J and V_J (one cp.async group)
-        if (ft < ng) {
-            const int st = fg & 3;
-            if (fg >= 4) mbar_wait(&r.empty[st], ((fg >> 2) - 1) & 1u);
-            const int row = 4 * wid + (lane >> 4), cc = (lane & 15) * 2;
-#pragma unroll
-            for (int t2 = 0; t2 < 2; ++t2) {
-                const int k = row + 2 * t2;
-                cp_async16_t(&r.ring[st][0][k][cc], Wp + (size_t)k * np + 32 * fJ + cc);
-                cp_async16_t(&r.ring[st][1][k][cc], Vp + (size_t)k * np + 32 * fJ + cc);
-            }
-            cp_async_mbar_arrive(&r.full[st]);
-            ++fg;
-            if (++fJ > group_last(ft)) { ++ft; fJ = Jt; }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    auto tile_to = [&](double *dst0, const double *src0, size_t pitch) {
-        const size_t sstep = 2 * pitch;
-        const double *s0 = src0 + (size_t)(lane >> 4) * pitch + (lane & 15) * 2;
-        const double *s1 = s0 + sstep, *s2 = s1 + sstep, *s3 = s2 + sstep;
-        double *dst = dst0 + (lane >> 4) * TSTR + (lane & 15) * 2;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            cp_async16_t(dst + (8 * k) * TSTR, s0);
-            cp_async16_t(dst + (8 * k + 2) * TSTR, s1);
-            cp_async16_t(dst + (8 * k + 4) * TSTR, s2);
-            cp_async16_t(dst + (8 * k + 6) * TSTR, s3);
-            s0 += 4 * sstep; s1 += 4 * sstep; s2 += 4 * sstep; s3 += 4 * sstep;
-        }
-    };
-    fill();
-    fill();
-    unsigned g = gu0;
-    const double *tv = Tv + tig * TSTR + 4 * grp;
-    const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
-    for (int t = 0; t < ng; ++t) {
-        const int I = Jt + 8 * t + wid;
-        const bool act = I < NB;
-        const int Jlast = group_last(t);
-        double fw[4][8];
-        if (act) {
-            // row operands: -W_I to registers, -V_I to the second tile; the first C tile (unless the
-            // previous group already prefetched it)
-            tile_to(Tv, Vp + 32 * I, np);
-            if (t == 0) tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * I, lda);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
-                const double2 w0 = pw2[0], w1 = pw2[1];
-                fw[0][ks] = -w0.x; fw[1][ks] = -w0.y; fw[2][ks] = -w1.x; fw[3][ks] = -w1.y;
-            }
-        }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-        __syncwarp();
-        if (act) {
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) Tv[lane * TSTR + rr] = -Tv[lane * TSTR + rr];
-        }
-        __syncwarp();
-        for (int J = Jt; J <= Jlast; ++J, ++g) {
-            const int st = g & 3;
-            const bool work = act && J <= I;
-            fill();                                                    // operands two steps ahead
-            asm volatile("cp.async.wait_group 1;\n" ::: "memory");    // everything but that fill: my C tile
-            __syncwarp();
-            double c0[4][4], c1[4][4];      // [x][y]: rows 4 grp + x, columns 8 y + 2 tig (+1)
-            if (work) {
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const double2 *q0 = reinterpret_cast<const double2 *>(tc + 8 * y * TSTR);
-                    const double2 *q1 = reinterpret_cast<const double2 *>(tc + (8 * y + 1) * TSTR);
-                    const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
-                    c0[0][y] = a0.x; c0[1][y] = a0.y; c0[2][y] = a1.x; c0[3][y] = a1.y;
-                    c1[0][y] = b0.x; c1[1][y] = b0.y; c1[2][y] = b1.x; c1[3][y] = b1.y;
-                }
-                // the tile buffer is refilled below: its loads have to have landed
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    asm volatile("" ::"d"(c0[0][y]), "d"(c0[1][y]), "d"(c0[2][y]), "d"(c0[3][y]), "d"(c1[0][y]), "d"(c1[1][y]),
-                                 "d"(c1[2][y]), "d"(c1[3][y]));
-            }
-            __syncwarp();
-            // next C tile of this row, or -- on its last step -- the first one of my row in the next group
-            if (act && J + 1 <= I) {
-                tile_to(Tw, A + (size_t)(32 * (J + 1)) * lda + 32 * I, lda);
-            } else if (J == min(I, Jlast) && t + 1 < ng && I + 8 < NB) {
-                tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * (I + 8), lda);
-            }
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-            mbar_wait(&r.full[st], (g >> 2) & 1u);
-            if (work) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const double2 va = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR);
-                    const double2 vb = *reinterpret_cast<const double2 *>(tv + 4 * ks * TSTR + 2);
-                    const double fv[4] = {va.x, va.y, vb.x, vb.y};
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const double bw = r.ring[st][0][4 * ks + tig][8 * y + grp];
-                        const double bv = r.ring[st][1][4 * ks + tig][8 * y + grp];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
-                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
-                        }
-                    }
-                }
-                double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    double2 *o0 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y) * lda);
-                    double2 *o1 = reinterpret_cast<double2 *>(cp0 + (size_t)(8 * y + 1) * lda);
-                    o0[0] = make_double2(c0[0][y], c0[1][y]);
-                    o0[1] = make_double2(c0[2][y], c0[3][y]);
-                    o1[0] = make_double2(c1[0][y], c1[1][y]);
-                    o1[1] = make_double2(c1[2][y], c1[3][y]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&r.empty[st]);
-        }
-    }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    gu = g;
     __syncthreads();
 }
 

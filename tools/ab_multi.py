@@ -15,6 +15,7 @@ wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N))
 work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
 band = torch.zeros((nb, N, 33), dtype=torch.float64, device=dev)
 out = {"N": N, "batch": nb}
+bands = {}
 for tag, env in (("one_cta_per_matrix", "0"),) if os.environ.get("ARCB200_SY2SB_VARIANT") else (("one_cta_per_matrix", "0"), ("many_ctas_per_matrix", "1")):
     os.environ["ARCB200_SY2SB_MULTI"] = env
     def run():
@@ -24,4 +25,12 @@ for tag, env in (("one_cta_per_matrix", "0"),) if os.environ.get("ARCB200_SY2SB_
     e0.record(); run(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 2
     out[tag] = {"ms": ms, "tflops": (4.0 / 3.0) * N ** 3 * nb / (ms * 1e-3) / 1e12}
+    bands[tag] = band.clone()
+if len(bands) == 2:
+    b0, b1 = bands.values()
+    out["band_maxdiff"] = float((b0 - b1).abs().max())
+    # eigenvalues of the first matrix from the band of the many-CTA path against LAPACK on the dense matrix
+    import scipy.linalg as sl
+    bb = b1[0].cpu().numpy().T.copy()          # (33, N) lower band storage
+    out["eig_err_multi_vs_lapack"] = float(np.abs(sl.eigvals_banded(bb, lower=True) - np.linalg.eigvalsh(A[0])).max() / np.abs(A[0]).max())
 print(json.dumps(out))
