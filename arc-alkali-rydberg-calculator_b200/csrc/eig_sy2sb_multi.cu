@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, in
         __syncthreads();
         unsigned gu = 0;
         if (PHASE == 1) s1_symm_ring(c, r, p, gu, (int)blockIdx.x, 1);
-        else s1_syr2k_ring(c, r, p, gu, (int)blockIdx.x, 1);
+        else s1_syr2k_ring(c, r, p, gu, (int)(gridDim.x - 1 - blockIdx.x), 1);      // longest row groups first
     }
 }
 

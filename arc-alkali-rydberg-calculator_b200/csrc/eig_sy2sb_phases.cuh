@@ -930,8 +930,10 @@ static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Rin
     const int Jt = p + 1, m = NB - (p + 1);
     const int ng = gfirst + (gcount < 0 ? ((m + 7) >> 3) - gfirst : gcount);    // this CTA's row groups: gfirst .. ng - 1
     const unsigned gu0 = gu;
-    // group t: block rows Jt + 8 t + wid, steps J = Jt .. min(Jt + 8 t + 7, NB - 1)
-    auto group_last = [&](int t) { return min(Jt + 8 * t + 7, NB - 1); };
+    // group t: block rows Jt + 8 t - pad + wid (those >= Jt), steps J = Jt .. Jt + 8 t + 7 - pad.  The partial group is
+    // the FIRST one (the shortest rows): at the end it would cost a full-length pass with most warps idle.
+    const int pad = (8 - (m & 7)) & 7;
+    auto group_last = [&](int t) { return Jt + 8 * t + 7 - pad; };
     __syncthreads();
     int ft = gfirst, fJ = Jt;                   // schedule position of the next operand fill
     unsigned fg = gu0;
@@ -972,15 +974,15 @@ static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Rin
     const double *tv = Tv + tig * TSTR + 4 * grp;
     const double *tc = Tw + (2 * tig) * TSTR + 4 * grp;
     for (int t = gfirst; t < ng; ++t) {
-        const int I = Jt + 8 * t + wid;
-        const bool act = I < NB;
+        const int I = Jt + 8 * t + wid - pad;
+        const bool act = I >= Jt;
         const int Jlast = group_last(t);
         double fw[4][8];
         if (act) {
             // row operands: -W_I to registers, -V_I to the second tile; the first C tile (unless the
             // previous group already prefetched it)
             tile_to(Tv, Vp + 32 * I, np);
-            if (t == gfirst) tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * I, lda);
+            if (t == gfirst || I - 8 < Jt) tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * I, lda);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const double2 *pw2 = reinterpret_cast<const double2 *>(Wp + (size_t)(4 * ks + tig) * np + 32 * I + 4 * grp);
@@ -1021,7 +1023,7 @@ static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Rin
             // next C tile of this row, or -- on its last step -- the first one of my row in the next group
             if (act && J + 1 <= I) {
                 tile_to(Tw, A + (size_t)(32 * (J + 1)) * lda + 32 * I, lda);
-            } else if (J == min(I, Jlast) && t + 1 < ng && I + 8 < NB) {
+            } else if (act && J == I && t + 1 < ng) {
                 tile_to(Tw, A + (size_t)(32 * Jt) * lda + 32 * (I + 8), lda);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
