@@ -64,6 +64,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sy2sb_phase_kernel(TsArgs a, in
     }
 }
 
+// Panel QR + T factor alone, two CTAs per SM (<= 128 registers, 93 KB of shared memory): the column loop is a
+// chain of block barriers and L2 round trips, so two matrices per SM overlap almost perfectly
+constexpr int QR_TWD = 32 * S1_TSTR;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) sy2sb_qr_kernel(TsArgs a, int p)
+{
+    const int mat = blockIdx.y;
+    double *slot = a.base + (size_t)mat * a.slot;
+    extern __shared__ double sm[];
+    S1Ctx c;
+    c.tid = threadIdx.x; c.wid = c.tid >> 5; c.lane = c.tid & 31; c.grp = c.lane >> 2; c.tig = c.lane & 3;
+    c.np = a.Npad; c.lda = a.Npad; c.NB = a.NB;
+    c.A = slot + a.oA; c.Wp = slot + a.oWp; c.Vp = slot + a.oVp; c.tt = slot + a.oTau; c.Tfac = slot + a.oTfac;
+    c.Bs = nullptr;
+    double *half2 = sm + WARPS * QR_TWD;
+    c.Ts = reinterpret_cast<double(*)[33]>(half2);
+    c.G = reinterpret_cast<double(*)[33]>(half2 + 1056);
+    c.M1 = nullptr;
+    double *small = half2 + 2 * 1056;
+    c.wv = reinterpret_cast<double(*)[32]>(small);
+    c.sred = reinterpret_cast<double(*)[16]>(small + 64);
+    c.taus = small + 96;
+    c.Tw = sm + c.wid * QR_TWD;
+    s1_panel_qr<WARPS, QR_TWD>(c, p);
+    s1_tfactor<WARPS>(c, p);
+}
+
 // compact lower band (N x N part) after the last panel; grid (blocks, nmat)
 __global__ void __launch_bounds__(256) band_extract_kernel(TsArgs a)
 {
@@ -91,6 +118,11 @@ int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launche
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_phase_kernel<W, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_qr = (size_t)(W * QR_TWD + 2 * 1056 + 128) * sizeof(double);
+    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sy2sb_qr_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qr));
+    // ARCB200_SY2SB_QR2 = 0: panel QR in the one-CTA-per-SM phase kernel (as before)
+    const char *eq = getenv("ARCB200_SY2SB_QR2");
+    const bool qr2 = !(eq && eq[0] == '0');
     int n = 0;
     const bool dbg = getenv("ARCB200_DEBUG_SYNC") != nullptr;
     auto check = [&](int phase, int p) {
@@ -106,7 +138,8 @@ int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launche
     if (check(-1, -1)) return -2;
     for (int p = 0; p < a.NB - 1; ++p) {
         const int groups = (a.NB - (p + 1) + W - 1) / W;
-        sy2sb_phase_kernel<W, 0><<<dim3(1, nmat), W * 32, smem, st>>>(a, p);
+        if (qr2) sy2sb_qr_kernel<W><<<dim3(1, nmat), W * 32, smem_qr, st>>>(a, p);
+        else sy2sb_phase_kernel<W, 0><<<dim3(1, nmat), W * 32, smem, st>>>(a, p);
         if (check(0, p)) return -2;
         sy2sb_phase_kernel<W, 1><<<dim3(groups, nmat), W * 32, smem, st>>>(a, p);
         if (check(1, p)) return -2;

@@ -27,8 +27,9 @@ struct S1Ctx {
     double *Tw;                   // this warp's two transit tiles
 };
 
-// Householder QR of the panel below the band (in place) + clean V panel
-template <int WARPS>
+// Householder QR of the panel below the band (in place) + clean V panel.  TWD = doubles of shared memory behind
+// c.Tw per warp (the chunk ring of phase B lives there)
+template <int WARPS, int TWD = 2 * 32 * S1_TSTR>
 __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
 {
     const int tid = c.tid, wid = c.wid, lane = c.lane, grp = c.grp, tig = c.tig;
@@ -154,7 +155,7 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
             // for the arithmetic, so only the thread's own copies have to be waited for.
             {
                 constexpr int SLOTW = (2 + KO) * 32;
-                constexpr int NSLOT = (2 * 32 * TSTR) / SLOTW;
+                constexpr int NSLOT = TWD / SLOTW;
                 constexpr int RD = (NSLOT - 2 < 8) ? NSLOT - 2 : 8;
                 double *ring = Tw;
                 auto issueB = [&](int ch) {

@@ -1583,6 +1583,10 @@ int eig_sb2st(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 {
     if (!S.L.two_stage) { arcb200_set_error("sb2st: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
+    // two warps per sweep (eig_sb2st_split.cu) up to N = 3072 (tools/ab_sb2st.py: 1027 x3 11.7 -> 10.4 ms, 2363 x296
+    // 112.0 -> 107.7, 1932 x148 39.5 -> 35.9, 4096 x20 149 -> 158); ARCB200_SB2ST_SPLIT = 0 / 1 forces one kernel
+    const char *es = getenv("ARCB200_SB2ST_SPLIT");
+    if (es ? es[0] != '0' : a.N <= 3072) return eig_sb2st_split(a, nmat, st, launches);
     const size_t smem = (size_t)(TS_WARPS * 32 * 33 + 2 * TS_WARPS * 32) * sizeof(double);
     ARCB200_CUDA_CHECK(cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sb2st_kernel<<<nmat, TS_THREADS, smem, st>>>(a);

@@ -51,5 +51,7 @@ static __device__ __forceinline__ void cp_async_wait_all_t()
 
 }  // namespace ts
 
+// bulge chasing with every sweep split between an E-chain warp and a D-block warp (eig_sb2st_split.cu)
+int eig_sb2st_split(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launches);
 // band reduction with per-panel kernels and many CTAs per matrix (large N, small batches)
 int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launches);
