@@ -51,6 +51,7 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
     constexpr int TSTR = S1_TSTR;
     const int m0 = 32 * (p + 1), col0 = 32 * p;
     const int nch = NB - (p + 1);
+    const int nc2 = (nch + 1) >> 1;                       // 64-row chunks of the panel QR
     double *P = A + (size_t)col0 * lda;                   // P[r + j*lda], r absolute
     const int Jt = p + 1;
     constexpr int SV = 32 / WARPS;
@@ -92,40 +93,41 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
         double tau = 0.0, scale = 0.0, beta = 0.0;
         for (int c = -1; c < 32; ++c) {
             const int rd = m0 + c, cn = c + 1, par = cn & 1;
-            // ---------------- phase A
+            // ---------------- phase A   (lane <-> two consecutive rows: 64-row chunks, 16-byte accesses)
             double ssq = 0.0;
             const double wcn = (c >= 0 && cn < 32) ? wv[c & 1][cn] : 0.0;
-            for (int ch0 = wid; ch0 < nch; ch0 += WARPS * 4) {
-                double pc[4], pn[4];
+            for (int ch0 = wid; ch0 < nc2; ch0 += WARPS * 4) {
+                double2 pc[4], pn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
-                    pc[u] = (c >= 0 && ch < nch) ? P[r + (size_t)c * lda] : 0.0;
-                    pn[u] = (cn < 32 && ch < nch) ? P[r + (size_t)cn * lda] : 0.0;
+                    const int ch = ch0 + WARPS * u, r = m0 + 64 * ch + 2 * lane;
+                    const bool ok = ch < nc2 && r < np;
+                    pc[u] = (c >= 0 && ok) ? *reinterpret_cast<const double2 *>(&P[r + (size_t)c * lda]) : make_double2(0.0, 0.0);
+                    pn[u] = (cn < 32 && ok) ? *reinterpret_cast<const double2 *>(&P[r + (size_t)cn * lda]) : make_double2(0.0, 0.0);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int ch = ch0 + WARPS * u, r = m0 + 32 * ch + lane;
-                    if (ch < nch) {
-                        double v = 0.0;
+                    const int ch = ch0 + WARPS * u, r = m0 + 64 * ch + 2 * lane;
+                    if (ch < nc2 && r < np) {
+                        double2 v = make_double2(0.0, 0.0);
                         if (c >= 0) {
-                            if (r == rd) {
-                                v = 1.0;
-                                P[r + (size_t)c * lda] = beta;
-                            } else if (r > rd) {
-                                v = pc[u] * scale;
-                                P[r + (size_t)c * lda] = v;
-                            }
-                            Vp[(size_t)c * np + r] = v;
+                            double2 o = pc[u];                   // rows above the diagonal of R stay as they are
+                            if (r == rd) { v.x = 1.0; o.x = beta; } else if (r > rd) { v.x = pc[u].x * scale; o.x = v.x; }
+                            if (r + 1 == rd) { v.y = 1.0; o.y = beta; } else if (r + 1 > rd) { v.y = pc[u].y * scale; o.y = v.y; }
+                            if (r + 1 >= rd) *reinterpret_cast<double2 *>(&P[r + (size_t)c * lda]) = o;
+                            *reinterpret_cast<double2 *>(&Vp[(size_t)c * np + r]) = v;
                         }
-                        if (cn < 32 && r >= rd) {
-                            double x = pn[u];
+                        if (cn < 32 && r + 1 >= rd) {
+                            double2 x = pn[u];
                             if (c >= 0) {
-                                x -= v * wcn;
-                                P[r + (size_t)cn * lda] = x;
+                                x.x -= v.x * wcn;                // v = 0 above row rd
+                                x.y -= v.y * wcn;
+                                *reinterpret_cast<double2 *>(&P[r + (size_t)cn * lda]) = x;
                             }
-                            if (r == rd + 1) sred[par][15] = x;
-                            if (r > rd + 1) ssq += x * x;
+                            if (r == rd + 1) sred[par][15] = x.x;
+                            if (r + 1 == rd + 1) sred[par][15] = x.y;
+                            if (r > rd + 1) ssq += x.x * x.x;
+                            if (r + 1 > rd + 1) ssq += x.y * x.y;
                         }
                     }
                 }
@@ -151,23 +153,24 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
             for (int k = 0; k < KO; ++k) g[k] = h[k] = 0.0;
             // the warp streams (column c, column cn, own columns) x all rows through a ring of
             // chunk slots in its transit-tile area with cp.async, RD chunks ahead: the pass is
-            // no longer a chain of exposed DRAM round trips.  lane <-> row for the copy and
+            // no longer a chain of exposed DRAM round trips.  lane <-> row pair for the copy and
             // for the arithmetic, so only the thread's own copies have to be waited for.
             {
-                constexpr int SLOTW = (2 + KO) * 32;
+                constexpr int SLOTW = (2 + KO) * 64;
                 constexpr int NSLOT = TWD / SLOTW;
-                constexpr int RD = (NSLOT - 2 < 8) ? NSLOT - 2 : 8;
+                constexpr int RD = (NSLOT - 1 < 4) ? NSLOT - 1 : 4;
+                static_assert(RD >= 1, "phase-B ring: at least two chunk slots per warp");
                 double *ring = Tw;
                 auto issueB = [&](int ch) {
-                    if (ch < nch) {
-                        const int r = m0 + 32 * ch + lane;
-                        double *dst = ring + (ch % NSLOT) * SLOTW + lane;
-                        if (c >= 0) cp_async8_t(dst, Vp + (size_t)c * np + r);
-                        cp_async8_t(dst + 32, P + r + (size_t)cn * lda);
+                    const int r = m0 + 64 * ch + 2 * lane;
+                    if (ch < nc2 && r < np) {
+                        double *dst = ring + (ch % NSLOT) * SLOTW + 2 * lane;
+                        if (c >= 0) cp_async16_t(dst, Vp + (size_t)c * np + r);
+                        cp_async16_t(dst + 64, P + r + (size_t)cn * lda);
 #pragma unroll
                         for (int k = 0; k < KO; ++k) {
                             const int j = wid + WARPS * k;
-                            if (j > cn) cp_async8_t(dst + 64 + 32 * k, P + r + (size_t)j * lda);
+                            if (j > cn) cp_async16_t(dst + 128 + 64 * k, P + r + (size_t)j * lda);
                         }
                     }
                     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -175,26 +178,29 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
 #pragma unroll 1
                 for (int ch = 0; ch < RD; ++ch) issueB(ch);
 #pragma unroll 1
-                for (int ch = 0; ch < nch; ++ch) {
+                for (int ch = 0; ch < nc2; ++ch) {
                     issueB(ch + RD);
                     asm volatile("cp.async.wait_group %0;\n" ::"n"(RD) : "memory");
-                    const int r = m0 + 32 * ch + lane;
-                    if (r >= rd) {
-                        const double *sl = ring + (ch % NSLOT) * SLOTW + lane;
-                        const double v = (c >= 0) ? sl[0] : 0.0;
-                        const double xc = sl[32];
-                        const double xg = (r > rd + 1) ? xc : 0.0;
+                    const int r = m0 + 64 * ch + 2 * lane;
+                    if (r + 1 >= rd && r < np) {
+                        const double *sl = ring + (ch % NSLOT) * SLOTW + 2 * lane;
+                        const double2 v = (c >= 0) ? *reinterpret_cast<const double2 *>(sl) : make_double2(0.0, 0.0);
+                        const double2 xc = *reinterpret_cast<const double2 *>(sl + 64);
+                        const double xg0 = (r > rd + 1) ? xc.x : 0.0;
+                        const double xg1 = (r + 1 > rd + 1) ? xc.y : 0.0;
 #pragma unroll
                         for (int k = 0; k < KO; ++k) {
                             const int j = wid + WARPS * k;
                             if (j > cn) {
-                                double x = sl[64 + 32 * k];
+                                double2 x = *reinterpret_cast<const double2 *>(sl + 128 + 64 * k);
                                 if (c >= 0) {
-                                    x -= v * wreg[k];
-                                    P[r + (size_t)j * lda] = x;
+                                    x.x -= v.x * wreg[k];        // v = 0 above row rd
+                                    x.y -= v.y * wreg[k];
+                                    *reinterpret_cast<double2 *>(&P[r + (size_t)j * lda]) = x;
                                 }
-                                g[k] += xg * x;
-                                if (r == rd + 1) h[k] = x;
+                                g[k] += xg0 * x.x + xg1 * x.y;
+                                if (r == rd + 1) h[k] = x.x;
+                                if (r + 1 == rd + 1) h[k] = x.y;
                             }
                         }
                     }
@@ -204,7 +210,7 @@ __device__ __forceinline__ void s1_panel_qr(const S1Ctx &c, int p)
 #pragma unroll
             for (int k = 0; k < KO; ++k) {
                 g[k] = warp_sum(g[k]);
-                h[k] = __shfl_sync(ARCB200_FULL_MASK, h[k], cn & 31);   // row m0 + cn: chunk 0, lane cn
+                h[k] = __shfl_sync(ARCB200_FULL_MASK, h[k], (cn >> 1) & 31);   // row m0 + cn: chunk 0, lane cn / 2
                 wreg[k] = tau_n * (h[k] + scale_n * g[k]);
                 if (lane == 0) wv[par][wid + WARPS * k] = wreg[k];
             }
