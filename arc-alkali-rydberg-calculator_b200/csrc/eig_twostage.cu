@@ -1518,26 +1518,23 @@ int eig_use_two_stage(int N)
 {
     const char *ev = getenv("ARCB200_TWO_STAGE");
     if (ev) return ev[0] == '1' && N >= 96;
-    return N >= 1024 && N <= 16384;
+    // measured (tools/ab_crossover.py, batches of 74 / 296 / 592): the two-stage path is 1.1-1.5x faster than the
+    // one-stage cluster kernel for every N from 128 to 1000
+    return N >= 128 && N <= 16384;
 }
 
 int eig_sy2sb(const EigSlots &S, int nmat, cudaStream_t st, int *launches)
 {
     if (!S.L.two_stage) { arcb200_set_error("sy2sb: layout without two-stage buffers"); return -1; }
     const TsArgs a = make_args(S);
-    // One CTA per matrix is the faster kernel per matrix (1.05 ms against 1.15 ms at N = 2363) but only in
-    // whole waves of one matrix per SM; a batch that leaves more than ~8 % of its last wave idle goes to
-    // the per-phase kernels with many CTAs per matrix (measured, tools/ab_multi.py: 74 matrices 109 ms
-    // against 155 ms, 125: 151 / 156, 250: 286 / 311, 296: 338 / 312).
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    const int waves = (nmat + sms - 1) / sms;
-    const char *em = getenv("ARCB200_SY2SB_MULTI");       // tuning knob: force 0 / 1
-    const bool multi = em ? (em[0] == '1') : ((double)nmat < 0.92 * (double)(waves * sms));
+    // The per-phase kernels (eig_sy2sb_multi.cu: panel QR at two CTAs per SM, symmetric product and rank-2k update
+    // with one CTA per 8 block rows) are the default for every batch: the row groups of all matrices balance over
+    // the SMs and the latency-bound QR phases of two matrices overlap on one SM (tools/ab_multi.py, one CTA per
+    // matrix against per-phase: 2363 x296 262.0 / 250.9 ms, x250 259 / 217.5, 1932 x296 156.7 / 149.3,
+    // 1100 x296 38.6 / 35.7, 651 x286 13.3 / 11.5, 10384 x8 8560 / 1263).  ARCB200_SY2SB_MULTI = 0 selects the
+    // one-CTA-per-matrix kernels below.
+    const char *em = getenv("ARCB200_SY2SB_MULTI");
+    const bool multi = !(em && em[0] == '0');
     if (multi) return eig_sy2sb_multi(a, nmat, st, launches);
     // Four kernels for whole waves of one matrix per SM, measured on C3 (N = 2363, 296 matrices;
     // profiles/r02_ab_sy2sb_variants_c3.json):

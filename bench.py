@@ -412,7 +412,7 @@ def roofline_c3(N, k, npts):
     achieved = flops / (sy_ms * 1e-3) / 1e12
     traffic = load_traffic("sy2sb_c3_per_matrix")
     roof = {"bound": "tensor",
-            "kernel": "sy2sb_ring_kernel (dense -> band: panel QR + symmetric product + rank-2k update; mma.sync.m8n8k4.f64 fed by mbarrier-guarded cp.async rings)",
+            "kernel": "band reduction dense -> band (per panel: sy2sb_qr_kernel + sy2sb_phase_kernel<1,2,3>: panel QR, symmetric product, W, rank-2k update; mma.sync.m8n8k4.f64 fed by mbarrier-guarded cp.async rings), all launches of one arcb200_sy2sb_batched call",
             "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma,
             "traffic": traffic * nb if traffic else None,
             "peak_source": "measured in this run: register-only mma.sync.m8n8k4.f64 loop (arcb200_dmma_peak); "

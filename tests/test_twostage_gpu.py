@@ -172,3 +172,38 @@ def test_window_edges_of_the_two_stage_range():
         A = _sym(np.random.default_rng(N), 1, N)
         w, Z = sweep.syevd_batched(A)
         _check_eig(A, w, Z)
+
+
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("N", [200, 410])
+def test_one_stage_forced(N):
+    """The one-stage cluster kernel (eig_sytrd.cu) is the default only below N = 128 since the two-stage path
+    won the crossover measurement; it stays selectable and has to stay correct."""
+    from arc_b200 import sweep
+    A = _sym(np.random.default_rng(N + 1), 3, N)
+    w, Z = _with_env({"ARCB200_TWO_STAGE": "0"}, lambda: sweep.syevd_batched(A))
+    _check_eig(A, w, Z)
+
+
+@pytest.mark.parametrize("env", [{"ARCB200_SB2ST_SPLIT": "0"}, {"ARCB200_SB2ST_PAIRS": "2"}, {"ARCB200_SB2ST_PAIRS": "4"},
+                                 {"ARCB200_SB2ST_PAIRS": "8"}, {"ARCB200_SY2SB_QR2": "0"}])
+@pytest.mark.parametrize("N", [129, 333, 1057])
+def test_bulge_chasing_and_qr_variants(N, env):
+    """Every bulge-chasing configuration (one warp per sweep; E-chain + D-block warp pairs, 2 / 4 / 8 sweeps per
+    CTA) and both panel-QR kernels of the per-phase band reduction, ragged sizes, against LAPACK."""
+    from arc_b200 import sweep
+    A = _sym(np.random.default_rng(N), 3, N)
+    w, Z = _with_env(dict(env, ARCB200_TWO_STAGE="1"), lambda: sweep.syevd_batched(A))
+    _check_eig(A, w, Z)

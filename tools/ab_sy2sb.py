@@ -28,8 +28,9 @@ wbytes = int(lib.arcb200_sweep_workspace_bytes(N, nb, N))
 work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
 out = {"N": N, "batch": nb}
 bands = {}
-for variant in ("lockstep", "wg", "fused", "ring"):
+for variant in ("lockstep", "wg", "fused", "ring", "per_phase"):
     os.environ["ARCB200_SY2SB_VARIANT"] = variant
+    os.environ["ARCB200_SY2SB_MULTI"] = "1" if variant == "per_phase" else "0"      # per_phase = the default path
     band = torch.zeros((nb, N, 33), dtype=torch.float64, device=dev)
 
     def run():
@@ -69,7 +70,7 @@ def band_eigs(bb):
 worst = 0.0
 for m in range(min(nb, 3)):
     wr = np.linalg.eigvalsh(A[m])
-    for v in ("wg", "fused", "ring"):
+    for v in ("wg", "fused", "ring", "per_phase"):
         worst = max(worst, float(np.abs(band_eigs(bands[v][m]) - wr).max() / np.abs(wr).max()))
 out["eig_err_worst_of_3_matrices_wg_fused"] = worst
 out["band_maxdiff_wg_vs_lockstep"] = float(np.abs(bands["wg"] - bands["lockstep"]).max())
@@ -77,5 +78,7 @@ out["band_maxdiff_fused_vs_lockstep"] = float(np.abs(bands["fused"] - bands["loc
 out["speedup_wg"] = out["lockstep"]["ms"] / out["wg"]["ms"]
 out["speedup_fused"] = out["lockstep"]["ms"] / out["fused"]["ms"]
 out["speedup_ring"] = out["lockstep"]["ms"] / out["ring"]["ms"]
+out["speedup_per_phase"] = out["lockstep"]["ms"] / out["per_phase"]["ms"]
+out["band_maxdiff_per_phase_vs_lockstep"] = float(np.abs(bands["per_phase"] - bands["lockstep"]).max())
 out["band_maxdiff_ring_vs_lockstep"] = float(np.abs(bands["ring"] - bands["lockstep"]).max())
 print(json.dumps(out))
