@@ -136,18 +136,60 @@ int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launche
         return 0;
     };
     if (check(-1, -1)) return -2;
+    // Sub-batches on internal streams: the phases of one sub-batch are serial, but the tail of every launch (row
+    // groups of different lengths, one CTA per SM) and the latency-bound QR launches are filled by the kernels of
+    // the other sub-batches (tools/ab_multi.py, 1 / 2 / 4 / 8 streams: 2363 x296 251.2 / 239.8 / 239.7 / 236.9 ms,
+    // 2363 x125 119.5 / 114.6 / 109.4 / 109.0, 651 x286 10.7 / 9.9 / 9.7 / 9.7, 410 x300 5.4 / 4.3 / 3.9 / 3.8).
+    // ARCB200_SY2SB_STREAMS = 1..8 overrides the choice below.
+    constexpr int MAXS = 8;
+    static cudaStream_t istream[MAXS];
+    static cudaEvent_t iev[MAXS + 1];
+    static int idev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (idev != dev) {
+        // (re)create for this device; a process drives one device (one rank per GPU)
+        for (int s = 0; s < MAXS; ++s) ARCB200_CUDA_CHECK(cudaStreamCreateWithFlags(&istream[s], cudaStreamNonBlocking));
+        for (int s = 0; s <= MAXS; ++s) ARCB200_CUDA_CHECK(cudaEventCreateWithFlags(&iev[s], cudaEventDisableTiming));
+        idev = dev;
+    }
+    int ns = nmat >= 256 ? 8 : (nmat >= 64 ? 4 : (nmat >= 16 ? 2 : 1));
+    const char *esn = getenv("ARCB200_SY2SB_STREAMS");
+    if (esn && esn[0] >= '1' && esn[0] <= '8') ns = esn[0] - '0';
+    if (ns > nmat) ns = nmat;
+    if (dbg) ns = 1;
+    cudaStream_t sst[MAXS];
+    TsArgs sa[MAXS];
+    int sn[MAXS];
+    if (ns > 1) ARCB200_CUDA_CHECK(cudaEventRecord(iev[MAXS], st));
+    for (int s = 0; s < ns; ++s) {
+        const int lo = (int)((long long)nmat * s / ns), hi = (int)((long long)nmat * (s + 1) / ns);
+        sa[s] = a;
+        sa[s].base = a.base + (size_t)lo * a.slot;
+        sn[s] = hi - lo;
+        sst[s] = ns > 1 ? istream[s] : st;
+        if (ns > 1) ARCB200_CUDA_CHECK(cudaStreamWaitEvent(sst[s], iev[MAXS], 0));
+    }
     for (int p = 0; p < a.NB - 1; ++p) {
         const int groups = (a.NB - (p + 1) + W - 1) / W;
-        if (qr2) sy2sb_qr_kernel<W><<<dim3(1, nmat), W * 32, smem_qr, st>>>(a, p);
-        else sy2sb_phase_kernel<W, 0><<<dim3(1, nmat), W * 32, smem, st>>>(a, p);
-        if (check(0, p)) return -2;
-        sy2sb_phase_kernel<W, 1><<<dim3(groups, nmat), W * 32, smem, st>>>(a, p);
-        if (check(1, p)) return -2;
-        sy2sb_phase_kernel<W, 2><<<dim3(1, nmat), W * 32, smem, st>>>(a, p);
-        if (check(2, p)) return -2;
-        sy2sb_phase_kernel<W, 3><<<dim3(groups, nmat), W * 32, smem, st>>>(a, p);
-        if (check(3, p)) return -2;
-        n += 4;
+        for (int s = 0; s < ns; ++s) {
+            if (qr2) sy2sb_qr_kernel<W><<<dim3(1, sn[s]), W * 32, smem_qr, sst[s]>>>(sa[s], p);
+            else sy2sb_phase_kernel<W, 0><<<dim3(1, sn[s]), W * 32, smem, sst[s]>>>(sa[s], p);
+            if (check(0, p)) return -2;
+            sy2sb_phase_kernel<W, 1><<<dim3(groups, sn[s]), W * 32, smem, sst[s]>>>(sa[s], p);
+            if (check(1, p)) return -2;
+            sy2sb_phase_kernel<W, 2><<<dim3(1, sn[s]), W * 32, smem, sst[s]>>>(sa[s], p);
+            if (check(2, p)) return -2;
+            sy2sb_phase_kernel<W, 3><<<dim3(groups, sn[s]), W * 32, smem, sst[s]>>>(sa[s], p);
+            if (check(3, p)) return -2;
+            n += 4;
+        }
+    }
+    if (ns > 1) {
+        for (int s = 0; s < ns; ++s) {
+            ARCB200_CUDA_CHECK(cudaEventRecord(iev[s], sst[s]));
+            ARCB200_CUDA_CHECK(cudaStreamWaitEvent(st, iev[s], 0));
+        }
     }
     band_extract_kernel<<<dim3(64, nmat), 256, 0, st>>>(a);
     ARCB200_LAUNCH_CHECK("sy2sb multi-CTA kernels");

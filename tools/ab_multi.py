@@ -16,7 +16,12 @@ work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
 band = torch.zeros((nb, N, 33), dtype=torch.float64, device=dev)
 out = {"N": N, "batch": nb}
 bands = {}
-for tag, env in (("one_cta_per_matrix", "0"),) if os.environ.get("ARCB200_SY2SB_VARIANT") else (("one_cta_per_matrix", "0"), ("many_ctas_per_matrix", "1")):
+cases = (("one_cta_per_matrix", "0"), ("many_ctas_per_matrix", "1"))
+if os.environ.get("ARCB200_SY2SB_VARIANT"):
+    cases = cases[:1]
+if os.environ.get("AB_ONLY") == "multi":
+    cases = cases[1:]
+for tag, env in cases:
     os.environ["ARCB200_SY2SB_MULTI"] = env
     def run():
         _lib.check(lib.arcb200_sy2sb_batched(0, _lib.stream_ptr(0), N, nb, _lib.ptr(d_A), _lib.ptr(band), _lib.ptr(work), wbytes, 0), "sy2sb")
