@@ -28,6 +28,7 @@
 namespace {
 
 constexpr double STEIN_CLUSTER_TOL = 1e-6;
+constexpr int SU = 4;             // rows per load batch of the inverse-iteration passes
 constexpr int STEIN_ITS = 2;      // eigenvalues are exact to eps |T|: the second iteration already converges (dstein)
 
 struct SteinArgs {
@@ -121,35 +122,53 @@ __global__ void __launch_bounds__(32) stein_prep_kernel(SteinArgs a)
     }
 }
 
-// grid = (ceil(2k / 128), nmat)
+// grid = (ceil(2k / 128), nmat).  d and e^2 are staged through shared memory in chunks of 256 rows (next chunk
+// prefetched into registers): read straight from global memory the dependent Sturm recurrence paid an L2 round
+// trip per row (warp-uniform loads of eight matrices per SM do not stay in L1) -- 29 ms of the 485 ms C3 step.
 __global__ void __launch_bounds__(128) stein_bisect_kernel(SteinArgs a)
 {
-    const int mat = blockIdx.y;
-    const int t = blockIdx.x * 128 + threadIdx.x;
+    constexpr int CH = 256;
+    __shared__ double sd[CH], se[CH];
+    const int mat = blockIdx.y, tid = threadIdx.x;
+    const int t = blockIdx.x * 128 + tid;
     double *slot = a.base + (size_t)mat * a.slot;
     const double *__restrict__ d = slot + a.oD;
     double *aux = slot + a.oAux;
     const double *__restrict__ e2 = aux + a.Npad;
     double *cand = aux + 2 * (size_t)a.Npad;
     const int ncand = (int)aux[SA_NCAND];
-    // whole warps leave together: the loads below are warp-uniform
-    if ((t & ~31) >= ncand) return;
+    if (blockIdx.x * 128 >= ncand) return;               // whole blocks leave together
     const int idx = (int)aux[SA_C0] + min(t, ncand - 1);
     const double pivmin = aux[SA_PIVMIN];
+    const double atol = 2.220446049250313e-16 * aux[SA_TN];
     double lo = aux[SA_GL], hi = aux[SA_GU];
     const int n = a.N;
+    auto ld_d = [&](int i) { return i < n ? d[i] : 0.0; };
+    auto ld_e = [&](int i) { return (i >= 1 && i < n) ? e2[i - 1] : 0.0; };     // row i uses e2[i - 1]; row 0 none
     for (int it = 0; it < 80; ++it) {
         const double mid = 0.5 * (lo + hi);
-        if (!(mid > lo && mid < hi)) break;              // interval is down to neighbouring doubles
-        // (lanes that are done keep evaluating until the whole warp is: the loop is uniform)
-        double q = d[0] - mid;
-        int cnt = q < 0.0;
-        for (int i = 1; i < n; ++i) {
-            if (fabs(q) < pivmin) q = -pivmin;
-            q = d[i] - mid - e2[i - 1] * __drcp_rn(q);     // sign sequence only: a rounded reciprocal is enough
-            cnt += q < 0.0;
+        // stop like dstebz with its default tolerances: interval below ulp |T| (the backward error of the
+        // tridiagonalisation) or down to neighbouring doubles
+        const bool live = mid > lo && mid < hi && (hi - lo) > atol;
+        if (!__syncthreads_or(live)) break;              // (threads that are done keep evaluating: the loop is uniform)
+        double q = 1.0;                                  // row 0: q = d[0] - mid - 0 / 1
+        int cnt = 0;
+        double nd0 = ld_d(tid), nd1 = ld_d(tid + 128), ne0 = ld_e(tid), ne1 = ld_e(tid + 128);
+        for (int c0 = 0; c0 < n; c0 += CH) {
+            __syncthreads();
+            sd[tid] = nd0; sd[tid + 128] = nd1; se[tid] = ne0; se[tid + 128] = ne1;
+            __syncthreads();
+            const int nx = c0 + CH;
+            nd0 = ld_d(nx + tid); nd1 = ld_d(nx + tid + 128); ne0 = ld_e(nx + tid); ne1 = ld_e(nx + tid + 128);
+            const int len = min(CH, n - c0);
+#pragma unroll 8
+            for (int i = 0; i < len; ++i) {
+                if (fabs(q) < pivmin) q = -pivmin;
+                q = sd[i] - mid - se[i] * __drcp_rn(q);       // sign sequence only: a rounded reciprocal is enough
+                cnt += q < 0.0;
+            }
         }
-        if (cnt > idx) hi = mid; else lo = mid;
+        if (live) { if (cnt > idx) hi = mid; else lo = mid; }
     }
     if (t < ncand) cand[t] = 0.5 * (lo + hi);
 }
@@ -234,13 +253,28 @@ __global__ void __launch_bounds__(128) stein_invit_kernel(SteinArgs a)
         // forward: x <- L^-1 P (scale * x); the start vector is generated on the fly
         const double sc = (it == 0) ? 1.0 : (n * tn * eps) / fmax(s1, 1e-300);
         double xc = (it == 0) ? stein_rand(0u, (unsigned)j, (unsigned)mat) * (n * tn * eps) / (0.5 * n) : x[0] * sc;
-        for (int i = 0; i < n - 1; ++i) {
-            const size_t o = (size_t)i * kp;
-            const double xn = (it == 0) ? stein_rand((unsigned)(i + 1), (unsigned)j, (unsigned)mat) * (n * tn * eps) / (0.5 * n)
-                                        : x[o + kp] * sc;
-            const double l = fl[o];
-            if (piv[o]) { x[o] = xn; xc = xc - l * xn; }
-            else { x[o] = xc; xc = xn - l * xc; }
+        // rows in batches of SU: the loads of a batch are issued before its dependent chain (a chain step is one
+        // FMA, a DRAM round trip per step left the pass at a third of the HBM rate)
+        for (int i0 = 0; i0 < n - 1; i0 += SU) {
+            double l[SU], xn[SU];
+            unsigned char pv[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int i = min(i0 + u, n - 2);
+                const size_t o = (size_t)i * kp;
+                l[u] = fl[o];
+                pv[u] = piv[o];
+                xn[u] = (it == 0) ? stein_rand((unsigned)(i + 1), (unsigned)j, (unsigned)mat) * (n * tn * eps) / (0.5 * n)
+                                  : x[o + kp] * sc;
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                if (i0 + u < n - 1) {
+                    const size_t o = (size_t)(i0 + u) * kp;
+                    if (pv[u]) { x[o] = xn[u]; xc = xc - l[u] * xn[u]; }
+                    else { x[o] = xc; xc = xn[u] - l[u] * xc; }
+                }
+            }
         }
         x[(size_t)(n - 1) * kp] = xc;
         // backward: x <- U^-1 x
@@ -248,14 +282,24 @@ __global__ void __launch_bounds__(128) stein_invit_kernel(SteinArgs a)
         x[(size_t)(n - 1) * kp] = x1;
         s1 = fabs(x1);
         s2 = x1 * x1;
-        for (int i = n - 2; i >= 0; --i) {
-            const size_t o = (size_t)i * kp;
-            const double v = (x[o] - fb[o] * x1 - fdu2[o] * x2) * fainv[o];
-            x[o] = v;
-            s1 += fabs(v);
-            s2 += v * v;
-            x2 = x1;
-            x1 = v;
+        for (int i0 = n - 2; i0 >= 0; i0 -= SU) {
+            double xo[SU], b[SU], du[SU], ai[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const size_t o = (size_t)max(i0 - u, 0) * kp;
+                xo[u] = x[o]; b[u] = fb[o]; du[u] = fdu2[o]; ai[u] = fainv[o];
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                if (i0 - u >= 0) {
+                    const double v = (xo[u] - b[u] * x1 - du[u] * x2) * ai[u];
+                    x[(size_t)(i0 - u) * kp] = v;
+                    s1 += fabs(v);
+                    s2 += v * v;
+                    x2 = x1;
+                    x1 = v;
+                }
+            }
         }
     }
     // ---- normalised eigenvector -> column j of Z (column-major, ld = Npad)
