@@ -16,7 +16,7 @@ for l in out.split("\n"):
         kern = re.sub(r"\(.*", "", kern)
         counts[kern] = collections.Counter()
         continue
-    m = re.search(r"/\*[0-9a-f]{4}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_]+)[.\s;]", l)
+    m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_]+)[.\s;]", l)
     if m and kern:
         counts[kern]["instr"] += 1
         for k in keys:
