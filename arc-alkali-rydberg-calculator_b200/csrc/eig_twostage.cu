@@ -1073,6 +1073,15 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, Q2_WARPS == 4 ? 2 : 1) q2_kerne
         if (tid < 32) taus[buf][tid] = pt;
     };
 
+    // Row staging (per warp, lane-private columns).  Block (G, t) works on the 63 rows Wb .. Wb + 62,
+    // Wb = 32 G + 1 + 32 t, from the bottom up; block (G, t + 1) on Wb + 32 .. Wb + 94.  Its lower 31 rows are
+    // results of this block and are forwarded through L (double-buffered), its 32 fresh rows are prefetched
+    // into F by cp.async while this block computes: only the first block of a group reads Z with exposed
+    // latency (direct loads), and every row is read from HBM once per group step instead of twice.
+    extern __shared__ double q2sm[];
+    double *F = q2sm + wid * (1024 + 2 * 992) + lane;
+    double *L0 = F + 1024;
+    int lb = 0;
     int G = ngroups - 1, t = 0, buf = 0;
     double pv[32 / Q2_WARPS], pt;
     fetch(G, t, pv, pt);
@@ -1085,18 +1094,46 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, Q2_WARPS == 4 ? 2 : 1) q2_kerne
         if (more) fetch(Gn, tn, pv, pt);
         if (act) {
             const int s0 = 32 * G;
+            const bool first = t == 0;                       // nothing forwarded / prefetched for this block
+            const bool next_same = more && Gn == G;          // the next block continues this group
+            const double *Lc = L0 + lb * 992;
+            double *Ln = L0 + (lb ^ 1) * 992;
             double zr[39];
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
                 const int Rb = s0 + 31 - 8 * sub - 6 + 32 * t;
                 if (sub == 0) {
+                    if (first) {
 #pragma unroll
-                    for (int x = 0; x < 39; ++x) zr[x] = Zc[(size_t)(Rb + x) * kp];
+                        for (int x = 0; x < 39; ++x) zr[x] = Zc[(size_t)(Rb + x) * kp];
+                    } else {
+                        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+                        for (int x = 0; x < 7; ++x) zr[x] = Lc[(24 + x) * 32];
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) zr[7 + x] = F[x * 32];
+                    }
+                    if (next_same) {
+                        // F is refilled: its reads above have to have completed
+#pragma unroll
+                        for (int x = 7; x < 39; x += 8)
+                            asm volatile("" ::"d"(zr[x]), "d"(zr[x + 1]), "d"(zr[x + 2]), "d"(zr[x + 3]), "d"(zr[x + 4]),
+                                         "d"(zr[x + 5]), "d"(zr[x + 6]), "d"(zr[x + 7]));
+                        const double *src = Zc + (size_t)(Rb + 39) * kp;       // rows Wb + 63 .. Wb + 94
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) cp_async8_t(F + x * 32, src + (size_t)x * kp);
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
                 } else {
 #pragma unroll
                     for (int x = 30; x >= 0; --x) zr[x + 8] = zr[x];
+                    if (first) {
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) zr[x] = Zc[(size_t)(Rb + x) * kp];
+                        for (int x = 0; x < 8; ++x) zr[x] = Zc[(size_t)(Rb + x) * kp];
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) zr[x] = Lc[(24 - 8 * sub + x) * 32];
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -1104,32 +1141,53 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, Q2_WARPS == 4 ? 2 : 1) q2_kerne
                     const double tau = taus[buf][sw];
                     if (tau != 0.0) {
                         const double2 *vv = reinterpret_cast<const double2 *>(&Vs[buf][sw][0]);
-                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                        // eight partial sums: the dependent FMA chains of the dot product are the critical path
+                        // (two warps per scheduler cannot hide them)
+                        double2 xv[16];
 #pragma unroll
-                        for (int l2 = 0; l2 < 16; l2 += 2) {
-                            const double2 x0 = vv[l2], x1 = vv[l2 + 1];
-                            d0 += x0.x * zr[7 - u + 2 * l2];
-                            d1 += x0.y * zr[7 - u + 2 * l2 + 1];
-                            d2 += x1.x * zr[7 - u + 2 * l2 + 2];
-                            d3 += x1.y * zr[7 - u + 2 * l2 + 3];
+                        for (int l2 = 0; l2 < 16; ++l2) xv[l2] = vv[l2];
+                        double d[8];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            d[2 * c] = xv[c].x * zr[7 - u + 2 * c];
+                            d[2 * c + 1] = xv[c].y * zr[7 - u + 2 * c + 1];
                         }
-                        const double dot = tau * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+                        for (int l2 = 4; l2 < 16; ++l2) {
+                            d[2 * (l2 & 3)] += xv[l2].x * zr[7 - u + 2 * l2];
+                            d[2 * (l2 & 3) + 1] += xv[l2].y * zr[7 - u + 2 * l2 + 1];
+                        }
+                        const double dot = tau * (((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7])));
 #pragma unroll
                         for (int l2 = 0; l2 < 16; ++l2) {
-                            const double2 x0 = vv[l2];
-                            zr[7 - u + 2 * l2] -= dot * x0.x;
-                            zr[7 - u + 2 * l2 + 1] -= dot * x0.y;
+                            zr[7 - u + 2 * l2] -= dot * xv[l2].x;
+                            zr[7 - u + 2 * l2 + 1] -= dot * xv[l2].y;
                         }
                     }
                 }
+                // finished rows: the lower 31 go to the next block of the group through L (it stores them when it
+                // is done with them), everything else -- and everything of a group's last block -- to global memory
                 if (sub < 3) {
+                    if (next_same) {
 #pragma unroll
-                    for (int x = 31; x < 39; ++x) Zc[(size_t)(Rb + x) * kp] = zr[x];
+                        for (int x = 31; x < 39; ++x) Ln[(x - 8 - 8 * sub) * 32] = zr[x];      // rows 23..30 / 15..22 / 7..14 of the next block
+                    } else {
+#pragma unroll
+                        for (int x = 31; x < 39; ++x) Zc[(size_t)(Rb + x) * kp] = zr[x];
+                    }
                 } else {
 #pragma unroll
-                    for (int x = 0; x < 39; ++x) Zc[(size_t)(Rb + x) * kp] = zr[x];
+                    for (int x = 0; x < 32; ++x) Zc[(size_t)(Rb + x) * kp] = zr[x];
+                    if (next_same) {
+#pragma unroll
+                        for (int x = 32; x < 39; ++x) Ln[(x - 32) * 32] = zr[x];               // rows 0..6 of the next block
+                    } else {
+#pragma unroll
+                        for (int x = 32; x < 39; ++x) Zc[(size_t)(Rb + x) * kp] = zr[x];
+                    }
                 }
             }
+            if (next_same) lb ^= 1;
         }
         if (more) stash(buf ^ 1, pv, pt);
         __syncthreads();
@@ -1603,7 +1661,9 @@ int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, c
     const int rowtiles = (S.L.Npad + 64) / 32, coltiles = a.kp / 32;
     zt_in_kernel<<<dim3(rowtiles, coltiles, nmat), 256, 0, st>>>(a);
     const int nslab = a.kp / 32;
-    q2_kernel<4><<<dim3((nslab + 3) / 4, nmat), 128, 0, st>>>(a);
+    const size_t q2smem = (size_t)4 * (1024 + 2 * 992) * sizeof(double);
+    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(q2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2smem));
+    q2_kernel<4><<<dim3((nslab + 3) / 4, nmat), 128, q2smem, st>>>(a);
     int nl = 3;
     if (with_q1 && S.L.NB >= 2) {
         // Q1 on the same row-major window (T factors were left in oTfac by the band reduction)
