@@ -1141,27 +1141,22 @@ __global__ void __launch_bounds__(Q2_WARPS * 32, Q2_WARPS == 4 ? 2 : 1) q2_kerne
                     const double tau = taus[buf][sw];
                     if (tau != 0.0) {
                         const double2 *vv = reinterpret_cast<const double2 *>(&Vs[buf][sw][0]);
-                        // eight partial sums: the dependent FMA chains of the dot product are the critical path
-                        // (two warps per scheduler cannot hide them)
-                        double2 xv[16];
+                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                        for (int l2 = 0; l2 < 16; ++l2) xv[l2] = vv[l2];
-                        double d[8];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            d[2 * c] = xv[c].x * zr[7 - u + 2 * c];
-                            d[2 * c + 1] = xv[c].y * zr[7 - u + 2 * c + 1];
+                        for (int l2 = 0; l2 < 16; l2 += 2) {
+                            const double2 x0 = vv[l2], x1 = vv[l2 + 1];
+                            d0 += x0.x * zr[7 - u + 2 * l2];
+                            d1 += x0.y * zr[7 - u + 2 * l2 + 1];
+                            d2 += x1.x * zr[7 - u + 2 * l2 + 2];
+                            d3 += x1.y * zr[7 - u + 2 * l2 + 3];
                         }
-#pragma unroll
-                        for (int l2 = 4; l2 < 16; ++l2) {
-                            d[2 * (l2 & 3)] += xv[l2].x * zr[7 - u + 2 * l2];
-                            d[2 * (l2 & 3) + 1] += xv[l2].y * zr[7 - u + 2 * l2 + 1];
-                        }
-                        const double dot = tau * (((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7])));
+                        // (eight partial sums instead of four: no gain, 57.3 against 56.2 ms on C3)
+                        const double dot = tau * ((d0 + d1) + (d2 + d3));
 #pragma unroll
                         for (int l2 = 0; l2 < 16; ++l2) {
-                            zr[7 - u + 2 * l2] -= dot * xv[l2].x;
-                            zr[7 - u + 2 * l2 + 1] -= dot * xv[l2].y;
+                            const double2 x0 = vv[l2];
+                            zr[7 - u + 2 * l2] -= dot * x0.x;
+                            zr[7 - u + 2 * l2 + 1] -= dot * x0.y;
                         }
                     }
                 }
