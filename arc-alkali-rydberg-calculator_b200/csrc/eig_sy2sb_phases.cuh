@@ -819,13 +819,17 @@ static __device__ __forceinline__ void s1_symm_ring(const S1Ctx &c, const S1Ring
     const int ng = gcount < 0 ? ((m + 7) >> 3) - gfirst : gcount;     // this CTA's row groups: gfirst .. gfirst + ng - 1
     const int S = ng * m;                       // steps: step u <-> (group gfirst + u / m, q = Jt + u % m)
     const unsigned gu0 = gu;
+    // step u <-> (group gfirst + u / m, column block Jt + u % m); one group per CTA (the per-phase kernels): no division
+    const bool one = ng == 1;
+    auto ugrp = [&](int u) { return one ? 0 : u / m; };
+    auto ucol = [&](int u) { return one ? u : u % m; };
     __syncthreads();
     auto fill = [&](int u) {                    // my four rows of V_q of step u (commits one cp.async group)
         if (u < S) {
             const unsigned g = gu0 + (unsigned)u;
             const int st = g & 3;
             if (g >= 4) mbar_wait(&r.empty[st], ((g >> 2) - 1) & 1u);
-            const int q = Jt + u % m;
+            const int q = Jt + ucol(u);
             const int row = 4 * wid + (lane >> 4), cc = (lane & 15) * 2;
             cp_async16_t(&r.ring[st][0][row][cc], Vp + (size_t)row * np + 32 * q + cc);
             cp_async16_t(&r.ring[st][0][row + 2][cc], Vp + (size_t)(row + 2) * np + 32 * q + cc);
@@ -835,7 +839,7 @@ static __device__ __forceinline__ void s1_symm_ring(const S1Ctx &c, const S1Ring
     };
     auto tile = [&](int u) {                    // my tile of step u into buffer u & 1 (commits one group)
         if (u < S) {
-            const int i = Jt + 8 * (gfirst + u / m) + wid, q = Jt + u % m;
+            const int i = Jt + 8 * (gfirst + ugrp(u)) + wid, q = Jt + ucol(u);
             if (i < NB) {
                 const int Ib = max(i, q), Jb = min(i, q);
                 // four running source pointers: a cp.async holds its address registers until the LSU has
@@ -872,7 +876,7 @@ static __device__ __forceinline__ void s1_symm_ring(const S1Ctx &c, const S1Ring
         const unsigned g = gu0 + (unsigned)u;
         const int st = g & 3;
         mbar_wait(&r.full[st], (g >> 2) & 1u);
-        const int i = Jt + 8 * (gfirst + u / m) + wid, q = Jt + u % m;
+        const int i = Jt + 8 * (gfirst + ugrp(u)) + wid, q = Jt + ucol(u);
         if (i < NB) {
             const double *tw = Tw + (u & 1) * (32 * TSTR);
             if (q <= i) {
@@ -962,18 +966,18 @@ static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Rin
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
     auto tile_to = [&](double *dst0, const double *src0, size_t pitch) {
+        // eight running pointers, each used twice: a cp.async holds its address registers until the LSU has read
+        // them, and that queue is long in this phase (16 tile stores per thread and step ahead of the copies)
         const size_t sstep = 2 * pitch;
-        const double *s0 = src0 + (size_t)(lane >> 4) * pitch + (lane & 15) * 2;
-        const double *s1 = s0 + sstep, *s2 = s1 + sstep, *s3 = s2 + sstep;
+        const double *s[8];
+        s[0] = src0 + (size_t)(lane >> 4) * pitch + (lane & 15) * 2;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s[k] = s[k - 1] + sstep;
         double *dst = dst0 + (lane >> 4) * TSTR + (lane & 15) * 2;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            cp_async16_t(dst + (8 * k) * TSTR, s0);
-            cp_async16_t(dst + (8 * k + 2) * TSTR, s1);
-            cp_async16_t(dst + (8 * k + 4) * TSTR, s2);
-            cp_async16_t(dst + (8 * k + 6) * TSTR, s3);
-            s0 += 4 * sstep; s1 += 4 * sstep; s2 += 4 * sstep; s3 += 4 * sstep;
-        }
+        for (int k = 0; k < 8; ++k) cp_async16_t(dst + (2 * k) * TSTR, s[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp_async16_t(dst + (16 + 2 * k) * TSTR, s[k] + 8 * sstep);
     };
     fill();
     fill();
