@@ -722,11 +722,12 @@ __device__ __forceinline__ void s1_syr2k_lockstep(const S1Ctx &c, int p, int gfi
                     for (int y = 0; y < 4; ++y) {
                         const double bw = Bs[buf][0][8 * y + grp][4 * ks + tig];
                         const double bv = Bs[buf][1][8 * y + grp][4 * ks + tig];
+                        // the two products of an accumulator four DMMAs apart (asm volatile keeps this order): issued
+                        // back to back the second waits for the first one's result
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
-                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
-                        }
+                        for (int x = 0; x < 4; ++x) dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
                     }
                 }
                 double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
@@ -1049,11 +1050,12 @@ static __device__ __forceinline__ void s1_syr2k_ring(const S1Ctx &c, const S1Rin
                     for (int y = 0; y < 4; ++y) {
                         const double bw = r.ring[st][0][4 * ks + tig][8 * y + grp];
                         const double bv = r.ring[st][1][4 * ks + tig][8 * y + grp];
+                        // the two products of an accumulator four DMMAs apart (asm volatile keeps this order): issued
+                        // back to back the second waits for the first one's result
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            dmma_t(c0[x][y], c1[x][y], fv[x], bw);
-                            dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
-                        }
+                        for (int x = 0; x < 4; ++x) dmma_t(c0[x][y], c1[x][y], fv[x], bw);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) dmma_t(c0[x][y], c1[x][y], fw[x][ks], bv);
                     }
                 }
                 double *cp0 = &A[32 * I + 4 * grp + (size_t)(32 * J + 2 * tig) * lda];
