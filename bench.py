@@ -322,7 +322,7 @@ def bench_full_sweeps(args, rank, world):
             F = np.linspace(0, 200, 2000)
             # warm-up on a slice, like C1's: the first use of a kernel variant in a process pays its lazy module
             # load (0.2 s here, once) -- not part of a sweep's cost
-            calc.diagonalise(F[: 37 * max(world, 1)], group=G)
+            calc.diagonalise(F[: min(len(F), 300 * max(world, 1))], group=G)      # two batches per rank: same kernel variants
             t_diag, _ = _wall(lambda: calc.diagonalise(F, group=G), world)
             record(name, len(calc.basisStates), len(F), t_def, t_diag, calc.last_sweep.kernel_launches)
             out["_" + name + "_calc"] = calc
