@@ -153,7 +153,8 @@ int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launche
         for (int s = 0; s <= MAXS; ++s) ARCB200_CUDA_CHECK(cudaEventCreateWithFlags(&iev[s], cudaEventDisableTiming));
         idev = dev;
     }
-    int ns = nmat >= 256 ? 8 : (nmat >= 64 ? 4 : (nmat >= 16 ? 2 : 1));
+    // (eight streams only pay for large matrices: 651 x286 and 410 x300 are as fast with four and half the launches)
+    int ns = (nmat >= 256 && a.N > 1024) ? 8 : (nmat >= 64 ? 4 : (nmat >= 16 ? 2 : 1));
     const char *esn = getenv("ARCB200_SY2SB_STREAMS");
     if (esn && esn[0] >= '1' && esn[0] <= '8') ns = esn[0] - '0';
     if (ns > nmat) ns = nmat;

@@ -1656,9 +1656,19 @@ int eig_q2_apply(const EigSlots &S, int nmat, const int32_t *d_sel0, int nsel, c
     const int rowtiles = (S.L.Npad + 64) / 32, coltiles = a.kp / 32;
     zt_in_kernel<<<dim3(rowtiles, coltiles, nmat), 256, 0, st>>>(a);
     const int nslab = a.kp / 32;
-    const size_t q2smem = (size_t)4 * (1024 + 2 * 992) * sizeof(double);
-    ARCB200_CUDA_CHECK(cudaFuncSetAttribute(q2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2smem));
-    q2_kernel<4><<<dim3((nslab + 3) / 4, nmat), 128, q2smem, st>>>(a);
+    // four slabs (128 eigenvector columns) per CTA, two CTAs per SM; batches that would leave SMs without a CTA
+    // (C5: 74 matrices x 250 vectors) get two slabs per CTA.  ARCB200_Q2_WARPS = 2 | 4 forces one.
+    const char *eqw = getenv("ARCB200_Q2_WARPS");
+    const bool q2small = eqw ? eqw[0] == '2' : (long long)nmat * ((nslab + 3) / 4) < 2 * 148;
+    if (q2small) {
+        const size_t q2smem = (size_t)2 * (1024 + 2 * 992) * sizeof(double);
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(q2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2smem));
+        q2_kernel<2><<<dim3((nslab + 1) / 2, nmat), 64, q2smem, st>>>(a);
+    } else {
+        const size_t q2smem = (size_t)4 * (1024 + 2 * 992) * sizeof(double);
+        ARCB200_CUDA_CHECK(cudaFuncSetAttribute(q2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2smem));
+        q2_kernel<4><<<dim3((nslab + 3) / 4, nmat), 128, q2smem, st>>>(a);
+    }
     int nl = 3;
     if (with_q1 && S.L.NB >= 2) {
         // Q1 on the same row-major window (T factors were left in oTfac by the band reduction)

@@ -198,11 +198,13 @@ def test_one_stage_forced(N):
 
 
 @pytest.mark.parametrize("env", [{"ARCB200_SB2ST_SPLIT": "0"}, {"ARCB200_SB2ST_PAIRS": "2"}, {"ARCB200_SB2ST_PAIRS": "4"},
-                                 {"ARCB200_SB2ST_PAIRS": "8"}, {"ARCB200_SY2SB_QR2": "0"}])
+                                 {"ARCB200_SB2ST_PAIRS": "8"}, {"ARCB200_SY2SB_QR2": "0"}, {"ARCB200_Q2_WARPS": "2"},
+                                 {"ARCB200_Q2_WARPS": "4"}, {"ARCB200_SY2SB_STREAMS": "1"}, {"ARCB200_SY2SB_STREAMS": "8"}])
 @pytest.mark.parametrize("N", [129, 333, 1057])
 def test_bulge_chasing_and_qr_variants(N, env):
     """Every bulge-chasing configuration (one warp per sweep; E-chain + D-block warp pairs, 2 / 4 / 8 sweeps per
-    CTA) and both panel-QR kernels of the per-phase band reduction, ragged sizes, against LAPACK."""
+    CTA), both panel-QR kernels and 1 / 8 internal streams of the per-phase band reduction, both CTA shapes of
+    the Q2 back-transform; ragged sizes, against LAPACK."""
     from arc_b200 import sweep
     A = _sym(np.random.default_rng(N), 3, N)
     w, Z = _with_env(dict(env, ARCB200_TWO_STAGE="1"), lambda: sweep.syevd_batched(A))
