@@ -512,30 +512,75 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
         arcb200_set_error("workspace too small for overlaps (add N*k doubles)");
         return -1;
     }
-    for (int p0 = 0; p0 < nR; p0 += batch) {
-        const int nmat = min(batch, nR - p0);
-        assemble_pair_kernel<<<dim3(ntiles, nmat), 256, 0, st>>>(
-            N, L.Npad, W.S.dbl, L.slot_doubles, L.oA, d_h0diag, norders, d_M, d_R, p0);
+    // One chunk of sweep points: assemble -> eigensolve -> epilogue in the slots [slot0, slot0 + nmat) on stream cs
+    auto run_chunk = [&](int p0, int nmat, int slot0, cudaStream_t cs) -> int {
+        WorkView V = W;
+        V.S.dbl = W.S.dbl + (size_t)slot0 * L.slot_doubles;
+        V.S.ints = W.S.ints + (size_t)slot0 * L.slot_ints;
+        V.S.gemm_probs = (char *)W.S.gemm_probs + (size_t)slot0 * EIG_MAX_NODES * EIG_PROB_BYTES;
+        V.sel0 = W.sel0 + slot0;
+        assemble_pair_kernel<<<dim3(ntiles, nmat), 256, 0, cs>>>(
+            N, L.Npad, V.S.dbl, L.slot_doubles, L.oA, d_h0diag, norders, d_M, d_R, p0);
         ++launches;
-        int rc = solve_batch(W, nmat, k, true, sigma, st, &launches);
+        int rc = solve_batch(V, nmat, k, true, sigma, cs, &launches);
         if (rc) return rc;
-        epilogue_kernel<<<dim3((k + 7) / 8, nmat), 256, 0, st>>>(
-            N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, L.oLam, W.sel0, k, opi, d_drive_w,
+        epilogue_kernel<<<dim3((k + 7) / 8, nmat), 256, 0, cs>>>(
+            N, L.Npad, V.S.dbl, L.slot_doubles, L.oQ1, L.oLam, V.sel0, k, opi, d_drive_w,
             topk <= MAXTOP ? topk : 0, contrib_max, d_y, d_hl, d_comp_c, d_comp_i, p0);
         ++launches;
         if (topk > MAXTOP) {
-            rc = launch_full_composition(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, nmat, topk,
-                                         contrib_max, d_comp_c, d_comp_i, p0, st);
+            rc = launch_full_composition(N, L.Npad, V.S.dbl, L.slot_doubles, L.oQ1, V.sel0, k, nmat, topk,
+                                         contrib_max, d_comp_c, d_comp_i, p0, cs);
             if (rc) return rc;
             ++launches;
         }
-        if (d_overlap) {
-            overlap_kernel<<<dim3((k + 15) / 16, (k + 15) / 16, nmat), 256, 0, st>>>(
-                N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, p0 == 0 ? nullptr : prevZ,
-                d_overlap, p0);
-            save_window_kernel<<<148, 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0,
-                                                    k, nmat - 1, prevZ);
-            launches += 2;
+        return 0;
+    };
+    // Experiment kept behind ARCB200_PIPELINE=1 (off by default): batches smaller than the SM count (C5 holds 74
+    // matrices in HBM; strong-scaling shards) leave SMs idle in every kernel that gives a matrix one CTA (bulge
+    // chasing, Q2, Q1: 29 % of the C5 step on half of the SMs).  Splitting such a batch into two half-batches on
+    // two streams lets the one-CTA-per-matrix stages of a chunk run beside the band reduction of the next -- but
+    // those stages take as long for 37 matrices as for 74 (latency bound per matrix), so the sweep got slower:
+    // C5 74 points 5.94 -> 7.13 s, C3 125 points 281 -> 283 ms, 74 points 186 -> 217 ms (tools/ab_pipeline.py).
+    static cudaStream_t pstream[2];
+    static cudaEvent_t pev[3];
+    static int pdev = -1;
+    const char *epl = getenv("ARCB200_PIPELINE");
+    const bool pipe = epl && epl[0] == '1' && L.two_stage && !d_overlap && batch >= 2;
+    if (pipe) {
+        if (pdev != device) {
+            for (int i = 0; i < 2; ++i) ARCB200_CUDA_CHECK(cudaStreamCreateWithFlags(&pstream[i], cudaStreamNonBlocking));
+            for (int i = 0; i < 3; ++i) ARCB200_CUDA_CHECK(cudaEventCreateWithFlags(&pev[i], cudaEventDisableTiming));
+            pdev = device;
+        }
+        ARCB200_CUDA_CHECK(cudaEventRecord(pev[2], st));
+        for (int i = 0; i < 2; ++i) ARCB200_CUDA_CHECK(cudaStreamWaitEvent(pstream[i], pev[2], 0));
+        const int half = (batch + 1) / 2;
+        int c = 0;
+        for (int p0 = 0; p0 < nR; ++c) {
+            const int h = c & 1;
+            const int nmat = min(h ? batch - half : half, nR - p0);
+            const int rc = run_chunk(p0, nmat, h ? half : 0, pstream[h]);
+            if (rc) return rc;
+            p0 += nmat;
+        }
+        for (int i = 0; i < 2; ++i) {
+            ARCB200_CUDA_CHECK(cudaEventRecord(pev[i], pstream[i]));
+            ARCB200_CUDA_CHECK(cudaStreamWaitEvent(st, pev[i], 0));
+        }
+    } else {
+        for (int p0 = 0; p0 < nR; p0 += batch) {
+            const int nmat = min(batch, nR - p0);
+            const int rc = run_chunk(p0, nmat, 0, st);
+            if (rc) return rc;
+            if (d_overlap) {
+                overlap_kernel<<<dim3((k + 15) / 16, (k + 15) / 16, nmat), 256, 0, st>>>(
+                    N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0, k, p0 == 0 ? nullptr : prevZ,
+                    d_overlap, p0);
+                save_window_kernel<<<148, 256, 0, st>>>(N, L.Npad, W.S.dbl, L.slot_doubles, L.oQ1, W.sel0,
+                                                        k, nmat - 1, prevZ);
+                launches += 2;
+            }
         }
     }
     ARCB200_LAUNCH_CHECK("pair sweep");

@@ -79,6 +79,29 @@ def test_pair_c3(gold_dir):
     _check(calc, g)
 
 
+def test_pair_sweep_half_batch_pipeline_matches_serial(gold_dir):
+    """ARCB200_PIPELINE=1 (two half-batches on two streams, an experiment that stays selectable) against the
+    default serial batches on the C3 operators: same energies and highlights."""
+    g = np.load(os.path.join(gold_dir, "pair_c3_golden.npz"))
+    calc = _build(g)
+    R = np.linspace(8.0, 2.0, 7)
+    res = {}
+    for env in ("0", "1"):
+        old = os.environ.get("ARCB200_PIPELINE")
+        os.environ["ARCB200_PIPELINE"] = env
+        try:
+            calc.diagonalise(R, 60)
+            res[env] = (np.array(calc.y), np.array(calc.highlight))
+        finally:
+            if old is None:
+                del os.environ["ARCB200_PIPELINE"]
+            else:
+                os.environ["ARCB200_PIPELINE"] = old
+    scale = np.abs(res["0"][0]).max()
+    assert np.abs(res["0"][0] - res["1"][0]).max() <= 1e-11 * scale
+    assert np.abs(res["0"][1] - res["1"][1]).max() <= 1e-6
+
+
 def test_pair_c5_class_large_basis():
     """BASELINE.json configs[4]: Rb 80D5/2+80D5/2, theta=pi/4, phi=0, Bz=1e-4 ->
     272 channels, N=10384.  One R point, k=250, against LAPACK on the host."""
