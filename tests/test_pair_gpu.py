@@ -99,7 +99,12 @@ def test_pair_sweep_half_batch_pipeline_matches_serial(gold_dir):
                 os.environ["ARCB200_PIPELINE"] = old
     scale = np.abs(res["0"][0]).max()
     assert np.abs(res["0"][0] - res["1"][0]).max() <= 1e-11 * scale
-    assert np.abs(res["0"][1] - res["1"][1]).max() <= 1e-6
+    for i in range(len(R)):
+        # a point sits in another slot of its batch, so inverse iteration starts from other random vectors:
+        # eigenvectors inside near-degenerate clusters rotate, the cluster sums of the highlight do not
+        a = _cluster_sums(res["0"][0][i], res["0"][1][i], 1e-6 * scale)
+        b = _cluster_sums(res["0"][0][i], res["1"][1][i], 1e-6 * scale)
+        assert np.abs(a[1:-1] - b[1:-1]).max() <= 1e-6, i
 
 
 def test_pair_c5_class_large_basis():
