@@ -244,7 +244,7 @@ int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_t batch,
 int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_t batch,
                           const double *d_d, const double *d_e, double *d_w, double *d_Q,
                           void *d_work, int64_t work_bytes, int32_t *h_launches);
-/* Stage 1 of the two-stage path alone (dense -> band of width 32, mid-sized N only; when the
+/* Stage 1 of the two-stage path alone (dense -> band of width 32, 128 <= N <= 16384; when the
  * two-stage path is active arcb200_sytrd_batched with cluster = 0 runs both of its stages and
  * returns the tridiagonal d, e; tau is then per band-reduction reflector).
  * d_band[b][j][d] = B[j+d][j], d = 0..32 (batch x N x 33). */
