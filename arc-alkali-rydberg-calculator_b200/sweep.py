@@ -83,7 +83,9 @@ def _pick_batch(N, npoints, nvec, device, batch=None):
     b = int(min(npoints, max(1, (frac * free) // per)))
     # one CTA (or a small cluster) per matrix: 148 matrices in flight fill the GPU
     # (two per SM while two CTAs' shared memory fits, N <= ~4000)
-    cap = 592 if N <= 512 else (296 if N <= 4000 else 148)
+    # small matrices: fewer, larger batches -- the sweep is launch-bound on the host (measured: C1 600 fields
+    # 12.7 k solves/s in two batches, 13.9 k in one; C4 singlet 4.4 k at 286 per batch, 4.7 k at 667)
+    cap = 1184 if N <= 512 else (740 if N <= 1024 else (296 if N <= 4000 else 148))
     b = max(1, min(b, cap))
     # equal chunks: a nearly empty tail pass costs a full sweep latency
     nchunks = -(-npoints // b)
