@@ -39,6 +39,25 @@ def printStateLetter(l):
     return "SPDFGHIKLMNOQRTUVWXYZ"[l] if l < 21 else " l=%d" % l
 
 
+def _unique_bounded(code):
+    """np.unique(code, return_index=True, return_inverse=True) for non-negative int64 codes; when
+    the codes are dense enough a lookup table replaces the sort (O(m) instead of O(m log m)).  The
+    representative index is that of the LAST occurrence (any occurrence serves the callers)."""
+    code = np.asarray(code, dtype=np.int64)
+    if not len(code):
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    R = int(code.max()) + 1
+    if R > max(1 << 22, 8 * len(code)):
+        return np.unique(code, return_index=True, return_inverse=True)
+    rep = np.full(R, -1, dtype=np.int64)
+    rep[code] = np.arange(len(code))
+    uc = np.flatnonzero(rep >= 0)
+    rank = np.empty(R, dtype=np.int64)
+    rank[uc] = np.arange(len(uc))
+    return uc, rep[uc], rank[code]
+
+
 class AlkaliAtom:
     """Data-backed atom.  `AlkaliAtom("Rubidium85")` or the named constructors below."""
 
@@ -254,68 +273,145 @@ class AlkaliAtom:
             n1, l1, j1, n2, l2, j2 = n2, l2, j2, n1, l1, j1
         return (round(n1), round(l1), round(2 * j1), round(n2), round(l2), round(2 * j2))
 
-    def precompute_radial(self, dipole_pairs=(), quadrupole_pairs=(), s=0.5,
-                          useLiterature=True):
-        """Evaluate all listed (n1,l1,j1,n2,l2,j2) elements in one GPU batch and memoise
-        them.  This is the batch seam that replaces the reference's sqlite memo
-        (seam B2).  Returns the number of newly computed elements."""
-        todo = []        # (memo dict, key, power)
-        seen = set()
-        for pairs, memo, power, ok in (
-                (dipole_pairs, self._dipole, 1, self._dipole_allowed),
-                (quadrupole_pairs, self._quadrupole, 2, self._quadrupole_allowed)):
-            for (n1, l1, j1, n2, l2, j2) in pairs:
-                if not ok(l1, j1, l2, j2):
-                    continue
-                key = self._ordered_key(n1, l1, j1, n2, l2, j2)
-                if key in memo or (power, key) in seen:
-                    continue
-                if power == 1 and useLiterature and key in self._lit:
-                    continue
-                seen.add((power, key))
-                todo.append((memo, key, power))
-        if not todo:
-            return 0
-        states, index = [], {}
-        pair_rows = np.zeros((len(todo), 3), dtype=np.int32)
-        for t, (memo, key, power) in enumerate(todo):
-            for slot, st in enumerate(((key[0], key[1], key[2] / 2.0),
-                                       (key[3], key[4], key[5] / 2.0))):
-                if st not in index:
-                    index[st] = len(states)
-                    states.append(self._state_record(*st))
-                pair_rows[t, slot] = index[st]
-            pair_rows[t, 2] = power
+    # ---- vector forms: whole tables at numpy speed (defineBasis of a 2000-state Stark basis asks
+    # for 1e5 elements; one Python call chain per element was most of its wall time)
+    @staticmethod
+    def _as_pairs(pairs):
+        """(n1, l1, j1, n2, l2, j2) rows as a contiguous float64 [m, 6] array (lists of tuples accepted)."""
+        if not isinstance(pairs, np.ndarray):
+            pairs = list(pairs)
+            if not pairs:
+                return np.zeros((0, 6))
+        return np.ascontiguousarray(pairs, dtype=np.float64).reshape(-1, 6)
+
+    @staticmethod
+    def _index_states(P):
+        """Rows (n1,l1,j1,n2,l2,j2) -> (S, ia, ib): the distinct (n, l, j) states as S[ns, 3] and,
+        per row, the indices of its two states."""
+        A = P.reshape(-1, 3)                              # rows alternate state 1, state 2
+        if not len(A):
+            return np.zeros((0, 3)), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        n, l, j2 = (np.rint(c).astype(np.int64) for c in (A[:, 0], A[:, 1], 2 * A[:, 2]))
+        code = ((n - n.min()) * (l.max() + 1) + l) * (j2.max() + 1) + j2
+        _uc, first, inv = _unique_bounded(code)
+        return A[first], inv[0::2], inv[1::2]
+
+    @staticmethod
+    def _allowed_cols(l1, j1, l2, j2, power):
+        """Selection rules of getRadialMatrixElement (aaf:1016-1019) / getQuadrupoleMatrixElement
+        (aaf:1134-1137) on columns."""
+        dl, dj = np.abs(l1 - l2), np.abs(j1 - j2)
+        if power == 1:
+            return (dl == 1) & (dj < 1.1)
+        return ((dl == 0) | (dl == 1) | (dl == 2)) & (dj < 2.1)
+
+    def _keys_from(self, S, lo, hi, s):
+        """Memo keys (n, l, 2j, n', l', 2j') of the elements S[lo] -> S[hi], as `_ordered_key` builds them."""
+        C = np.empty((len(S), 3), dtype=np.int64)
+        C[:, 0], C[:, 1], C[:, 2] = np.rint(S[:, 0]), np.rint(S[:, 1]), np.rint(2 * S[:, 2])
+        return list(map(tuple, np.hstack([C[lo], C[hi]]).tolist()))
+
+    def _unique_elements(self, S, ia, ib, power, s):
+        """Distinct allowed elements among S[ia] <-> S[ib]: (ok mask over the rows, memo keys of the
+        distinct elements with the lower-energy state first (aaf:1021-1037), index of every allowed
+        row into them)."""
+        ok = self._allowed_cols(S[ia, 1], S[ia, 2], S[ib, 1], S[ib, 2], power)
+        if not ok.any():
+            return ok, [], np.zeros(0, dtype=np.int64)
+        ia, ib = ia[ok], ib[ok]
+        es = 0.5 if s is None else s
+        E = np.array([self.getEnergy(int(round(t[0])), int(round(t[1])), float(t[2]), s=es) for t in S])
+        swap = E[ia] > E[ib]
+        lo, hi = np.where(swap, ib, ia), np.where(swap, ia, ib)
+        ucode, _first, inv = _unique_bounded(lo * len(S) + hi)
+        return ok, self._keys_from(S, ucode // len(S), ucode % len(S), s), inv
+
+    def _compute_elements(self, keys, powers, s=0.5):
+        """Values of the elements `keys` (memo keys, lower-energy state first; powers[i] = 1 dipole,
+        2 quadrupole): ONE batched Numerov run over the distinct states, one integral launch."""
+        K = np.array(keys, dtype=np.int64).reshape(-1, 6)
+        S, ia, ib = self._index_states(K.astype(np.float64) * np.array([1, 1, .5, 1, 1, .5]))
+        states = [self._state_record(int(t[0]), int(t[1]), float(t[2])) for t in S]
+        pair_rows = np.empty((len(keys), 3), dtype=np.int32)
+        pair_rows[:, 0], pair_rows[:, 1], pair_rows[:, 2] = ia, ib, powers
         rb = _radial.RadialBatch(np.array(states), normalise=True, device=self.device)
-        if getattr(self, "radial_group", None) is not None and len(todo) >= 1024:
+        if getattr(self, "radial_group", None) is not None and len(keys) >= 1024:
             # collective: every rank of the group builds the same table
             vals = rb.integrals_sharded(pair_rows, self.radial_group).cpu().numpy()
-        elif not self.fast_radial or len(todo) < self.gram_threshold:
+        elif not self.fast_radial or len(keys) < self.gram_threshold:
             # sorted by (power, lower-energy state): the warps of a CTA share psi_a / r_a through L1
             order = np.lexsort((pair_rows[:, 1], pair_rows[:, 0], pair_rows[:, 2]))
-            vals = np.empty(len(todo))
+            vals = np.empty(len(keys))
             vals[order] = rb.integrals(pair_rows[order])
         else:
             # tensor-core path: one Gram block per ((l,j) of state a, (l,j) of state b, power)
             groups = {}
-            for t, (memo, key, power) in enumerate(todo):
+            for t, (key, power) in enumerate(zip(keys, powers)):
                 groups.setdefault((key[1], key[2], key[4], key[5], power), []).append(t)
-            blocks, where = [], [None] * len(todo)
+            blocks, where = [], [None] * len(keys)
             for g, (gk, ts) in enumerate(groups.items()):
                 ra = sorted(set(int(pair_rows[t, 0]) for t in ts))
                 cb = sorted(set(int(pair_rows[t, 1]) for t in ts))
-                ia = {s_: q for q, s_ in enumerate(ra)}
-                ib = {s_: q for q, s_ in enumerate(cb)}
+                ia_ = {s_: q for q, s_ in enumerate(ra)}
+                ib_ = {s_: q for q, s_ in enumerate(cb)}
                 blocks.append((ra, cb, gk[4]))
                 for t in ts:
-                    where[t] = (g, ia[int(pair_rows[t, 0])] * len(cb) + ib[int(pair_rows[t, 1])])
+                    where[t] = (g, ia_[int(pair_rows[t, 0])] * len(cb) + ib_[int(pair_rows[t, 1])])
             out, offs, _nref = rb.gram_refined_device(blocks, thresh=_radial.GRAM_REFINE_THRESH)
             out = out.cpu().numpy()
             vals = np.array([out[offs[g] + e] for g, e in where])
         self.gpu_kernel_launches += rb.kernel_launches
-        for (memo, key, power), v in zip(todo, vals):
-            memo[key] = float(v)
-        return len(todo)
+        return np.asarray(vals, dtype=np.float64).tolist()
+
+    def radial_elements_indexed(self, S, ia, ib, power=1, s=0.5, useLiterature=True):
+        """Vector form of getRadialMatrixElement (power 1) / getQuadrupoleMatrixElement (power 2)
+        for the state pairs S[ia[k]] <-> S[ib[k]] (S = [ns, 3] rows (n, l, j)): one value per k,
+        0 where the selection rules forbid the element.  Elements missing from the memo are
+        computed in ONE GPU batch."""
+        S = np.asarray(S, dtype=np.float64).reshape(-1, 3)
+        ia, ib = np.asarray(ia, dtype=np.int64), np.asarray(ib, dtype=np.int64)
+        out = np.zeros(len(ia))
+        ok, keys, inv = self._unique_elements(S, ia, ib, power, s)
+        if not keys:
+            return out
+        memo = self._dipole if power == 1 else self._quadrupole
+        lit = self._lit if (power == 1 and useLiterature) else {}
+        missing = [k for k in keys if k not in memo and k not in lit]
+        if missing:
+            memo.update(zip(missing, self._compute_elements(missing, [power] * len(missing), s)))
+        if lit:
+            vals = np.array([lit[k][0] if k in lit else memo[k] for k in keys])
+        else:
+            vals = np.array(list(map(memo.__getitem__, keys)))
+        out[ok] = vals[inv]
+        return out
+
+    def radial_elements(self, pairs, power=1, s=0.5, useLiterature=True):
+        """radial_elements_indexed for explicit (n1, l1, j1, n2, l2, j2) rows."""
+        S, ia, ib = self._index_states(self._as_pairs(pairs))
+        return self.radial_elements_indexed(S, ia, ib, power, s=s, useLiterature=useLiterature)
+
+    def precompute_radial(self, dipole_pairs=(), quadrupole_pairs=(), s=0.5,
+                          useLiterature=True):
+        """Evaluate all listed (n1,l1,j1,n2,l2,j2) elements (lists of tuples or [m, 6] arrays) in
+        one GPU batch and memoise them.  This is the batch seam that replaces the reference's
+        sqlite memo (seam B2).  Returns the number of newly computed elements."""
+        fresh = []
+        for pairs, memo, power in ((dipole_pairs, self._dipole, 1), (quadrupole_pairs, self._quadrupole, 2)):
+            P = self._as_pairs(pairs)
+            if not len(P):
+                fresh.append([])
+                continue
+            _ok, keys, _inv = self._unique_elements(*self._index_states(P), power, s)
+            lit = self._lit if (power == 1 and useLiterature) else {}
+            fresh.append([k for k in keys if k not in memo and k not in lit])
+        nd, nq = len(fresh[0]), len(fresh[1])
+        if nd + nq == 0:
+            return 0
+        vals = self._compute_elements(fresh[0] + fresh[1], [1] * nd + [2] * nq, s)
+        self._dipole.update(zip(fresh[0], vals[:nd]))
+        self._quadrupole.update(zip(fresh[1], vals[nd:]))
+        return nd + nq
 
     def getRadialMatrixElement(self, n1, l1, j1, n2, l2, j2, s=0.5, useLiterature=True):
         """Radial dipole element in a0*e (alkali_atom_functions.py:978-1105)."""
@@ -508,46 +604,59 @@ class DivalentAtom(AlkaliAtom):
             n1, l1, j1, n2, l2, j2 = n2, l2, j2, n1, l1, j1
         return (round(n1), round(l1), j1, round(n2), round(l2), j2, s)
 
-    def _semiclassical_params(self, key, kind):
-        n1, l1, j1, n2, l2, j2, s = key
-        if kind == 1:   # aaf:2693-2699: nu from energies
-            nu = np.sqrt(-self.scaledRydbergConstant / self.getEnergy(n1, l1, j1, s=s))
-            nu1 = np.sqrt(-self.scaledRydbergConstant / self.getEnergy(n2, l2, j2, s=s))
-        else:           # aaf:2749-2750: nu from quantum defects
-            nu = n1 - self.getQuantumDefect(n1, l1, j1, s=s)
-            nu1 = n2 - self.getQuantumDefect(n2, l2, j2, s=s)
-        return (nu, nu1, l1, l2)
+    def _semiclassical_params(self, keys, kind, s):
+        """(nu, nu', l, l') per memo key: effective quantum numbers from the energies for the dipole
+        formula (aaf:2693-2699), from the quantum defects for the quadrupole one (aaf:2749-2750);
+        every distinct state is evaluated once."""
+        K = np.array([k[:6] for k in keys], dtype=np.float64).reshape(-1, 6)
+        S, ia, ib = self._index_states(K)
+        if kind == 1:
+            e = np.array([self.getEnergy(int(t[0]), int(t[1]), float(t[2]), s=s) for t in S])
+            nu = np.sqrt(-self.scaledRydbergConstant / e)
+        else:
+            nu = np.array([int(t[0]) - self.getQuantumDefect(int(t[0]), int(t[1]), float(t[2]), s=s) for t in S])
+        return np.stack([nu[ia], nu[ib], K[:, 1], K[:, 4]], axis=1)
+
+    @staticmethod
+    def _allowed_cols(l1, j1, l2, j2, power):
+        dl = np.abs(l1 - l2)
+        if power == 1:                                    # div:404-407 (its dj test is j2 - j2 == 0)
+            return dl == 1
+        return ((dl == 0) | (dl == 1) | (dl == 2)) & (np.abs(j1 - j2) < 2.1)
+
+    def _keys_from(self, S, lo, hi, s):
+        """Memo keys (n, l, j, n', l', j', s), as `_ordered` builds them."""
+        n, l = np.rint(S[:, 0]).astype(np.int64), np.rint(S[:, 1]).astype(np.int64)
+        return list(zip(n[lo].tolist(), l[lo].tolist(), S[lo, 2].tolist(),
+                        n[hi].tolist(), l[hi].tolist(), S[hi, 2].tolist(), [s] * len(lo)))
+
+    def _compute_elements(self, keys, powers, s=None):
+        """Semiclassical elements (aaf:2683-2802) of the memo keys, one launch per kind."""
+        powers = np.asarray(powers)
+        vals = np.zeros(len(keys))
+        for kind in (1, 2):
+            sel = np.flatnonzero(powers == kind)
+            if len(sel):
+                params = self._semiclassical_params([keys[i] for i in sel], kind, s)
+                vals[sel] = _radial.semiclassical_table(params, kind, device=self.device)
+                self.gpu_kernel_launches += 1
+        return vals.tolist()
+
+    def radial_elements_indexed(self, S, ia, ib, power=1, s=None, useLiterature=True):
+        if s is None:
+            raise ValueError("You must specify total angular momentum s explicitly.")
+        return super().radial_elements_indexed(S, ia, ib, power, s=s, useLiterature=useLiterature)
+
+    def radial_elements(self, pairs, power=1, s=None, useLiterature=True):
+        if s is None:
+            raise ValueError("You must specify total angular momentum s explicitly.")
+        return super().radial_elements(pairs, power, s=s, useLiterature=useLiterature)
 
     def precompute_radial(self, dipole_pairs=(), quadrupole_pairs=(), s=None,
                           useLiterature=True):
         if s is None:
             raise ValueError("You must specify total angular momentum s explicitly.")
-        n_new = 0
-        for pairs, memo, kind in ((dipole_pairs, self._dipole, 1),
-                                  (quadrupole_pairs, self._quadrupole, 2)):
-            keys, seen = [], set()
-            for (n1, l1, j1, n2, l2, j2) in pairs:
-                dl = abs(l1 - l2)
-                if kind == 1 and dl != 1:                 # div:404-407 (dj = |j2-j2| == 0)
-                    continue
-                if kind == 2 and not (dl in (0, 1, 2) and abs(j1 - j2) < 2.1):
-                    continue
-                key = self._ordered(n1, l1, j1, n2, l2, j2, s)
-                if key in memo or key in seen:
-                    continue
-                if kind == 1 and useLiterature and key in self._lit:
-                    continue
-                seen.add(key)
-                keys.append(key)
-            if not keys:
-                continue
-            params = np.array([self._semiclassical_params(k, kind) for k in keys])
-            vals = _radial.semiclassical_table(params, kind, device=self.device)
-            self.gpu_kernel_launches += 1
-            for k, v in zip(keys, vals):
-                memo[k] = float(v)
-            n_new += len(keys)
-        return n_new
+        return super().precompute_radial(dipole_pairs, quadrupole_pairs, s=s, useLiterature=useLiterature)
 
     def getRadialMatrixElement(self, n1, l1, j1, n2, l2, j2, s=None, useLiterature=True):
         """divalent_atom_functions.py:369-464."""

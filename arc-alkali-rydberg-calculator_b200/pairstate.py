@@ -113,6 +113,11 @@ class PairCompositionView:
             yield self[r]
 
 
+def _kron(A, B):
+    """numpy.kron for two matrices (same products, without its generic-rank bookkeeping)."""
+    return (A[:, None, :, None] * B[None, :, None, :]).reshape(A.shape[0] * B.shape[0], A.shape[1] * B.shape[1])
+
+
 class PairStateInteractions:
     def __init__(self, atom, n, l, j, nn, ll, jj, m1, m2, interactionsUpTo=1, s=0.5,
                  s2=None, atom2=None, reference_6j_table_quirk=True):
@@ -233,7 +238,7 @@ class PairStateInteractions:
         if af is None or af[0] == 0.0:
             return np.zeros(shape)
         elem, terms = af
-        return elem * sum(f * np.kron(A, B) for f, A, B in terms)
+        return elem * sum(f * _kron(A, B) for f, A, B in terms)
 
     def _isCoupled(self, n, l, j, nn, ll, jj, n1, l1, j1, n2, l2, j2, limit):
         """Scalar form of calculations_atom_pairstate.py:625-710 (returns c1+c2 or False)."""
@@ -608,35 +613,33 @@ class PairStateInteractions:
         ok &= (np.abs(nA[I] - nA[J]) <= k) & (np.abs(nB[I] - nB[J]) <= k)
         I, J, c1, c2 = I[ok], J[ok], c1[ok], c2[ok]
 
-        # ---- all radial elements of both atoms in one GPU batch per atom
-        def want(nq, lq, jq, cs):
-            dip, quad = [], []
-            for a, b, c in zip(I, J, cs):
-                t = (int(nq[a]), int(lq[a]), float(jq[a]), int(nq[b]), int(lq[b]), float(jq[b]))
-                (dip if c == 1 else quad).append(t)
-            return dip, quad
-        for atom, (dip, quad), spin in ((self.atom1, want(nA, lA, jA, c1), self.s1),
-                                        (self.atom2, want(nB, lB, jB, c2), self.s2)):
+        # ---- all radial elements of both atoms in one GPU batch per atom (vector form: the memo is
+        # filled by one precompute_radial call per atom, then read back for all couplings at once)
+        def radial(atom, nq, lq, jq, cs, spin):
+            P = np.stack([nq[I], lq[I], jq[I], nq[J], lq[J], jq[J]], axis=1)
+            dip, quad = cs == 1, cs == 2
             before = atom.gpu_kernel_launches
             if getattr(atom, "divalent", False):
-                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad, s=spin)
+                atom.precompute_radial(dipole_pairs=P[dip], quadrupole_pairs=P[quad], s=spin)
             else:
-                atom.precompute_radial(dipole_pairs=dip, quadrupole_pairs=quad)
+                atom.precompute_radial(dipole_pairs=P[dip], quadrupole_pairs=P[quad])
             self.gpu_kernel_launches += atom.gpu_kernel_launches - before
+            S = np.stack([nq, lq, jq], axis=1)
+            r = np.zeros(len(I))
+            r[dip] = atom.radial_elements_indexed(S, I[dip], J[dip], 1, s=spin)
+            r[quad] = atom.radial_elements_indexed(S, I[quad], J[quad], 2, s=spin)
+            return r
+        r1 = radial(self.atom1, nA, lA, jA, c1, self.s1)
+        r2 = radial(self.atom2, nB, lB, jB, c2, self.s2)
 
+        # _atomLightAtomCoupling (alkali_atom_functions.py:4123-4129), GHz m^(c1+c2+1)
         a0 = physical_constants["Bohr radius"][0]
-        cons = [[[], [], []] for _ in range(2 * up - 1)]
-        for a, b, ca, cb in zip(I, J, c1, c2):
-            r1 = self.atom1.getRadialCoupling(int(nA[a]), int(lA[a]), float(jA[a]),
-                                              int(nA[b]), int(lA[b]), float(jA[b]), s=self.s1)
-            r2 = self.atom2.getRadialCoupling(int(nB[a]), int(lB[a]), float(jB[a]),
-                                              int(nB[b]), int(lB[b]), float(jB[b]), s=self.s2)
-            # _atomLightAtomCoupling (alkali_atom_functions.py:4123-4129), GHz m^(c1+c2+1)
-            val = (C_e ** 2 / (4.0 * pi * epsilon_0) * r1 * r2 * a0 ** (int(ca) + int(cb))) \
-                / C_h * 1.0e-9
-            cons[ca + cb - 2][0].append(val)
-            cons[ca + cb - 2][1].append(a)
-            cons[ca + cb - 2][2].append(b)
+        a0pow = np.array([a0 ** c for c in range(5)])
+        val = (C_e ** 2 / (4.0 * pi * epsilon_0) * r1 * r2 * a0pow[c1 + c2]) / C_h * 1.0e-9
+        cons = []
+        for o in range(2 * up - 1):
+            m = (c1 + c2 - 2) == o
+            cons.append((val[m], I[m], J[m]))
         coupling = [csr_matrix((c[0], (c[1], c[2])), shape=(dim, dim)) for c in cons]
         return states, coupling
 
@@ -663,12 +666,18 @@ class PairStateInteractions:
         opi = 0
         index = np.zeros(nch + 1, dtype=np.int64)   # cast to the reference's int16 after the size check
         prod_idx = []           # per channel: index of each basis state in the full m1 x m2 product
+        mcache = {}
+
+        def mgrid(jq):          # m = j, j-1, ..., -j exactly as the reference's np.linspace(j, -j, 2j+1)
+            if jq not in mcache:
+                mcache[jq] = list(np.linspace(jq, -jq, round(1 + 2 * jq)))
+            return mcache[jq]
         for i, ch in enumerate(self.channel):
             index[i] = len(self.basisStates)
             pidx = []
             ja, jb = ch[2], ch[5]
-            for m1c in np.linspace(ja, -ja, round(1 + 2 * ja)):
-                for m2c in np.linspace(jb, -jb, round(1 + 2 * jb)):
+            for m1c in mgrid(ja):
+                for m2c in mgrid(jb):
                     if (not limitBasisToMj) or (abs(originalMj - m1c - m2c) < 0.1):
                         self.basisStates.append([ch[0], ch[1], ch[2], m1c, ch[3], ch[4], ch[5], m2c])
                         self.matrixElement.append(i)
@@ -731,11 +740,11 @@ class PairStateInteractions:
                         else:
                             elem, terms = af
                             if trivial:
-                                B = elem * sum(f * np.kron(A, Bm) for f, A, Bm in terms)
+                                B = elem * sum(f * _kron(A, Bm) for f, A, Bm in terms)
                             else:
                                 D1, D2 = wgd.get(chi[2]), wgd.get(chi[5])
                                 D3, D4 = wgd.get(chj[2]), wgd.get(chj[5])
-                                B = elem * sum(f * np.kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
+                                B = elem * sum(f * _kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
                                                for f, A, Bm in terms)
                                 B = B.real
                             blk = B[np.ix_(prod_idx[jjc], prod_idx[ii])]     # rows: j states, cols: i states

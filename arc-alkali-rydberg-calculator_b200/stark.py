@@ -9,6 +9,7 @@ import numpy as np
 from scipy.constants import physical_constants, h as C_h, e as C_e
 
 from .wigner import CG
+from .atoms import _unique_bounded
 from . import sweep as _sweep
 
 
@@ -109,46 +110,46 @@ class StarkMap:
         self.basisStates = states
         self.indexOfCoupledState = indexOfCoupledState
 
-        # --- batch seam: every |dl|=1 pair goes to the GPU radial table at once
+        # --- batch seam: every |dl|=1 pair goes to the GPU radial table at once (vector form:
+        # index arrays instead of one Python call chain per matrix element)
+        S = np.array([st[:3] for st in states], dtype=np.float64).reshape(dimension, 3)
         by_l = {}
         for idx, st in enumerate(states):
             by_l.setdefault(st[1], []).append(idx)
-        pairs = []
+        pa, pb = [], []
         for l1, idxs in by_l.items():
-            for idx2 in by_l.get(l1 + 1, []):
-                for idx1 in idxs:
-                    pairs.append((idx1, idx2))
+            up = by_l.get(l1 + 1)
+            if up:
+                A, B = np.meshgrid(np.array(idxs), np.array(up), indexing="ij")
+                pa.append(A.ravel())
+                pb.append(B.ravel())
+        pa = np.concatenate(pa) if pa else np.zeros(0, dtype=np.int64)
+        pb = np.concatenate(pb) if pb else np.zeros(0, dtype=np.int64)
+        ii, jj = np.minimum(pa, pb), np.maximum(pa, pb)          # matrix element (ii, jj), ii < jj
         before = self.atom.gpu_kernel_launches
-        want = [(states[a][0], states[a][1], states[a][2],
-                 states[b][0], states[b][1], states[b][2]) for a, b in pairs]
-        if getattr(self.atom, "divalent", False):
-            self.atom.precompute_radial(dipole_pairs=want, s=s)
-        else:
-            self.atom.precompute_radial(dipole_pairs=want)
+        radial = self.atom.radial_elements_indexed(S, ii, jj, 1, s=s)
         self.gpu_kernel_launches += self.atom.gpu_kernel_launches - before
 
         mat1 = np.zeros((dimension, dimension), dtype=np.double)
         mat2 = np.zeros((dimension, dimension), dtype=np.double)
         zeeman = {}                                   # depends on (l, j, mj) only
-        for ii in range(dimension):
-            kz = (states[ii][1], states[ii][2], states[ii][3])
+        for i in range(dimension):
+            kz = (states[i][1], states[i][2], states[i][3])
             if kz not in zeeman:
                 zeeman[kz] = self.atom.getZeemanEnergyShift(kz[0], kz[1], kz[2], self.Bz, s=self.s) / C_h * 1.0e-9
-            mat1[ii][ii] = (self.atom.getEnergy(states[ii][0], states[ii][1], states[ii][2],
-                                                s=self.s) * C_e / C_h * 1e-9 + zeeman[kz])
-        ang = {}
-        for a, b in pairs:
-            ii, jj = (a, b) if a < b else (b, a)
-            k = (states[ii][1], states[ii][2], states[jj][1], states[jj][2])
-            if k not in ang:
-                ang[k] = efield_angular(states[ii][1], states[ii][2], mj,
-                                        states[jj][1], states[jj][2], mj, s=self.s)
-            coupling = (self.atom.getRadialMatrixElement(
-                states[ii][0], states[ii][1], states[ii][2],
-                states[jj][0], states[jj][1], states[jj][2], s=self.s)
-                * physical_constants["Bohr radius"][0] * C_e * ang[k]) * 1.0e-9 / C_h
-            mat2[jj][ii] = coupling
-            mat2[ii][jj] = coupling
+            mat1[i][i] = (self.atom.getEnergy(states[i][0], states[i][1], states[i][2],
+                                              s=self.s) * C_e / C_h * 1e-9 + zeeman[kz])
+        if len(ii):
+            # the angular factor depends on (l, j, l', j') only: one evaluation per distinct key
+            lj, cls = np.unique(S[:, 1:3], axis=0, return_inverse=True)       # (l, j) classes of the states
+            cls = cls.ravel()
+            ukey, _first, inv = _unique_bounded(cls[ii] * len(lj) + cls[jj])
+            ang = np.array([efield_angular(int(lj[k // len(lj), 0]), lj[k // len(lj), 1], mj,
+                                           int(lj[k % len(lj), 0]), lj[k % len(lj), 1], mj, s=self.s)
+                            for k in ukey])
+            coupling = (radial * physical_constants["Bohr radius"][0] * C_e * ang[inv]) * 1.0e-9 / C_h
+            mat2[jj, ii] = coupling
+            mat2[ii, jj] = coupling
         self.mat1, self.mat2 = mat1, mat2
         return 0
 

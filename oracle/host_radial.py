@@ -31,38 +31,25 @@ def patch_atom_with_oracle(atom, procs=1):
             d[k] = getattr(atom, k)[l] if l < 4 else 0.0
         return d
 
-    def precompute_radial(dipole_pairs=(), quadrupole_pairs=(), s=0.5, useLiterature=True):
-        todo = []
-        for pairs, memo, power, ok in ((dipole_pairs, atom._dipole, 1, atom._dipole_allowed),
-                                       (quadrupole_pairs, atom._quadrupole, 2, atom._quadrupole_allowed)):
-            for (n1, l1, j1, n2, l2, j2) in pairs:
-                if not ok(l1, j1, l2, j2):
-                    continue
-                key = atom._ordered_key(n1, l1, j1, n2, l2, j2)
-                if key in memo or (power == 1 and useLiterature and key in atom._lit):
-                    continue
-                memo[key] = None
-                todo.append((memo, key, power))
+    def compute_elements(keys, powers, s=0.5):
+        """Stand-in for AlkaliAtom._compute_elements: memo keys (n, l, 2j, n', l', 2j'), lower-energy
+        state first, and their powers -> values from the oracle."""
+        todo = list(zip(keys, powers))
         if procs <= 1 or len(todo) < 4 * procs:
-            for memo, key, power in todo:
-                a, b = sp(key[0], key[1], key[2] / 2.0), sp(key[3], key[4], key[5] / 2.0)
-                memo[key] = oracle.radial_integral(a, b, power)
-        else:
-            import multiprocessing as mp
-            params = dict(alphaC=atom.alphaC, alpha=atom.alpha, Z=atom.Z,
-                          mu=(atom.mass - 9.1093837139e-31) / atom.mass,
-                          a1=atom.a1, a2=atom.a2, a3=atom.a3, a4=atom.a4, rc=atom.rc)
-            jobs = []
-            for memo, key, power in todo:
-                sa = (key[0], key[1], key[2] / 2.0)
-                sb = (key[3], key[4], key[5] / 2.0)
-                jobs.append((params, sa + (atom.getEnergy(*sa) / 27.211386245981,),
-                             sb + (atom.getEnergy(*sb) / 27.211386245981,), power))
-            oracle._lib()          # build liboracle.so once, before forking
-            with mp.get_context("fork").Pool(procs) as pool:
-                vals = pool.map(_element_worker, jobs, chunksize=max(1, len(jobs) // (8 * procs)))
-            for (memo, key, power), v in zip(todo, vals):
-                memo[key] = v
-        return len(todo)
-    atom.precompute_radial = precompute_radial
+            return [oracle.radial_integral(sp(k[0], k[1], k[2] / 2.0), sp(k[3], k[4], k[5] / 2.0), int(p))
+                    for k, p in todo]
+        import multiprocessing as mp
+        params = dict(alphaC=atom.alphaC, alpha=atom.alpha, Z=atom.Z,
+                      mu=(atom.mass - 9.1093837139e-31) / atom.mass,
+                      a1=atom.a1, a2=atom.a2, a3=atom.a3, a4=atom.a4, rc=atom.rc)
+        jobs = []
+        for key, power in todo:
+            sa = (key[0], key[1], key[2] / 2.0)
+            sb = (key[3], key[4], key[5] / 2.0)
+            jobs.append((params, sa + (atom.getEnergy(*sa) / 27.211386245981,),
+                         sb + (atom.getEnergy(*sb) / 27.211386245981,), int(power)))
+        oracle._lib()          # build liboracle.so once, before forking
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(_element_worker, jobs, chunksize=max(1, len(jobs) // (8 * procs)))
+    atom._compute_elements = compute_elements
     return atom

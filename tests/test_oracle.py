@@ -84,12 +84,12 @@ def test_oracle_semiclassical_matches_golden(gold_dir):
     atom = arc_b200.Strontium88()
     for n1, l1, j1, n2, l2, j2, s, val in g["dipole"][:20]:
         key = atom._ordered(int(n1), int(l1), j1, int(n2), int(l2), j2, s)
-        p = atom._semiclassical_params(key, 1)
+        p = atom._semiclassical_params([key], 1, s)[0]
         v = oracle.semiclassical_dipole(*p)
         assert abs(v - val) <= 1e-10 * max(1.0, abs(val))
     for n1, l1, j1, n2, l2, j2, s, val in g["quadrupole"][:20]:
         key = atom._ordered(int(n1), int(l1), j1, int(n2), int(l2), j2, s)
-        p = atom._semiclassical_params(key, 2)
+        p = atom._semiclassical_params([key], 2, s)[0]
         v = oracle.semiclassical_quadrupole(*p)
         assert abs(v - val) <= 1e-10 * max(1.0, abs(val))
 
