@@ -16,7 +16,7 @@ import numpy as np
 from scipy.constants import physical_constants, h as C_h, e as C_e
 
 from . import sweep as _sweep
-from .stark import efield_angular
+from .stark import efield_angular, stark_couplings  # noqa: F401
 
 
 class StarkBasisGenerator:
@@ -123,40 +123,21 @@ class StarkBasisGenerator:
         reference).  All radial elements come from one GPU batch."""
         states = self.basisStates
         dimension = len(states)
-        by_l = {}
-        for idx, st in enumerate(states):
-            by_l.setdefault(st[1], []).append(idx)
-        pairs = [(a, b) for l1, idxs in by_l.items() for b in by_l.get(l1 + 1, []) for a in idxs]
-        want = [(states[a][0], states[a][1], states[a][2],
-                 states[b][0], states[b][1], states[b][2]) for a, b in pairs]
         before = self.atom.gpu_kernel_launches
-        if getattr(self.atom, "divalent", False):
-            self.atom.precompute_radial(dipole_pairs=want, s=self.s)
-        else:
-            self.atom.precompute_radial(dipole_pairs=want)
+        ii, jj, radial, ang = stark_couplings(self.atom, states, self.mj, self.s)
         self.gpu_kernel_launches += self.atom.gpu_kernel_launches - before
 
         self.bareEnergies = np.zeros((dimension), dtype=np.double)
         self.V = np.zeros((dimension, dimension), dtype=np.double)
-        for ii in range(dimension):
-            self.bareEnergies[ii] = (
-                self.atom.getEnergy(states[ii][0], states[ii][1], states[ii][2], s=self.s)
+        for i in range(dimension):
+            self.bareEnergies[i] = (
+                self.atom.getEnergy(states[i][0], states[i][1], states[i][2], s=self.s)
                 * C_e / C_h
-                + self.atom.getZeemanEnergyShift(states[ii][1], states[ii][2], states[ii][3],
+                + self.atom.getZeemanEnergyShift(states[i][1], states[i][2], states[i][3],
                                                  self.Bz, s=self.s) / C_h)
-        ang = {}
-        for a, b in pairs:
-            ii, jj = (a, b) if a < b else (b, a)
-            k = (states[ii][1], states[ii][2], states[jj][1], states[jj][2])
-            if k not in ang:
-                ang[k] = efield_angular(states[ii][1], states[ii][2], self.mj,
-                                        states[jj][1], states[jj][2], self.mj, s=self.s)
-            coupling = 0.5 * (self.atom.getRadialMatrixElement(
-                states[ii][0], states[ii][1], states[ii][2],
-                states[jj][0], states[jj][1], states[jj][2], s=self.s)
-                * physical_constants["Bohr radius"][0] * C_e * ang[k]) / C_h
-            self.V[jj][ii] = coupling
-            self.V[ii][jj] = coupling
+        coupling = 0.5 * (radial * physical_constants["Bohr radius"][0] * C_e * ang) / C_h
+        self.V[jj, ii] = coupling
+        self.V[ii, jj] = coupling
         self.H = np.diag(self.bareEnergies)
         self.targetEnergy = self.bareEnergies[self.indexOfCoupledState]
 

@@ -55,6 +55,38 @@ def efield_angular(l1, j1, mj1, l2, j2, mj2, s=0.5):
     return sumPart
 
 
+def stark_couplings(atom, states, mj, s):
+    """Every |dl| = 1 pair of the basis `states` ([n, l, j, ...] rows) in vector form: index arrays
+    (ii, jj) with ii < jj, the radial dipole elements (ONE GPU batch for those not memoised yet) and
+    the angular factors `efield_angular(l_ii, j_ii, mj, l_jj, j_jj, mj)` -- evaluated once per distinct
+    (l, j, l', j').  Shared by StarkMap.defineBasis and StarkBasisGenerator (Shirley)."""
+    dimension = len(states)
+    S = np.array([st[:3] for st in states], dtype=np.float64).reshape(dimension, 3)
+    by_l = {}
+    for idx, st in enumerate(states):
+        by_l.setdefault(st[1], []).append(idx)
+    pa, pb = [], []
+    for l1, idxs in by_l.items():
+        up = by_l.get(l1 + 1)
+        if up:
+            A, B = np.meshgrid(np.array(idxs), np.array(up), indexing="ij")
+            pa.append(A.ravel())
+            pb.append(B.ravel())
+    if not pa:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, np.zeros(0), np.zeros(0)
+    pa, pb = np.concatenate(pa), np.concatenate(pb)
+    ii, jj = np.minimum(pa, pb), np.maximum(pa, pb)
+    radial = atom.radial_elements_indexed(S, ii, jj, 1, s=s)
+    lj, cls = np.unique(S[:, 1:3], axis=0, return_inverse=True)           # (l, j) classes of the states
+    cls = cls.ravel()
+    ukey, _first, inv = _unique_bounded(cls[ii] * len(lj) + cls[jj])
+    ang = np.array([efield_angular(int(lj[k // len(lj), 0]), lj[k // len(lj), 1], mj,
+                                   int(lj[k % len(lj), 0]), lj[k % len(lj), 1], mj, s=s)
+                    for k in ukey])
+    return ii, jj, radial, ang[inv]
+
+
 class StarkMap:
     """Stark maps: basis |n l j mj>, H(F) = mat1 + F * mat2, eigensolve per field."""
 
@@ -110,24 +142,10 @@ class StarkMap:
         self.basisStates = states
         self.indexOfCoupledState = indexOfCoupledState
 
-        # --- batch seam: every |dl|=1 pair goes to the GPU radial table at once (vector form:
-        # index arrays instead of one Python call chain per matrix element)
-        S = np.array([st[:3] for st in states], dtype=np.float64).reshape(dimension, 3)
-        by_l = {}
-        for idx, st in enumerate(states):
-            by_l.setdefault(st[1], []).append(idx)
-        pa, pb = [], []
-        for l1, idxs in by_l.items():
-            up = by_l.get(l1 + 1)
-            if up:
-                A, B = np.meshgrid(np.array(idxs), np.array(up), indexing="ij")
-                pa.append(A.ravel())
-                pb.append(B.ravel())
-        pa = np.concatenate(pa) if pa else np.zeros(0, dtype=np.int64)
-        pb = np.concatenate(pb) if pb else np.zeros(0, dtype=np.int64)
-        ii, jj = np.minimum(pa, pb), np.maximum(pa, pb)          # matrix element (ii, jj), ii < jj
+        # --- batch seam: every |dl|=1 pair goes to the GPU radial table at once (index arrays
+        # instead of one Python call chain per matrix element)
         before = self.atom.gpu_kernel_launches
-        radial = self.atom.radial_elements_indexed(S, ii, jj, 1, s=s)
+        ii, jj, radial, ang = stark_couplings(self.atom, states, mj, s)
         self.gpu_kernel_launches += self.atom.gpu_kernel_launches - before
 
         mat1 = np.zeros((dimension, dimension), dtype=np.double)
@@ -139,17 +157,9 @@ class StarkMap:
                 zeeman[kz] = self.atom.getZeemanEnergyShift(kz[0], kz[1], kz[2], self.Bz, s=self.s) / C_h * 1.0e-9
             mat1[i][i] = (self.atom.getEnergy(states[i][0], states[i][1], states[i][2],
                                               s=self.s) * C_e / C_h * 1e-9 + zeeman[kz])
-        if len(ii):
-            # the angular factor depends on (l, j, l', j') only: one evaluation per distinct key
-            lj, cls = np.unique(S[:, 1:3], axis=0, return_inverse=True)       # (l, j) classes of the states
-            cls = cls.ravel()
-            ukey, _first, inv = _unique_bounded(cls[ii] * len(lj) + cls[jj])
-            ang = np.array([efield_angular(int(lj[k // len(lj), 0]), lj[k // len(lj), 1], mj,
-                                           int(lj[k % len(lj), 0]), lj[k % len(lj), 1], mj, s=self.s)
-                            for k in ukey])
-            coupling = (radial * physical_constants["Bohr radius"][0] * C_e * ang[inv]) * 1.0e-9 / C_h
-            mat2[jj, ii] = coupling
-            mat2[ii, jj] = coupling
+        coupling = (radial * physical_constants["Bohr radius"][0] * C_e * ang) * 1.0e-9 / C_h
+        mat2[jj, ii] = coupling
+        mat2[ii, jj] = coupling
         self.mat1, self.mat2 = mat1, mat2
         return 0
 

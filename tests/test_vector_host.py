@@ -1,0 +1,144 @@
+"""CPU tests of the vector host path (no GPU): `defineBasis` assembles its matrices from index
+arrays and whole-table radial look-ups (atoms.radial_elements_indexed); here every entry is
+rebuilt through the reference-shaped per-element call chain
+(`_eFieldCouplingDivE` -> `getRadialMatrixElement`, `getRadialCoupling`,
+calculations_atom_single.py:650-666, alkali_atom_functions.py:2260-2298, 4123-4129) and has to
+match bit for bit.  The GPU compute hook `_compute_elements` is replaced by a deterministic
+function of the memo key, so both routes see the same radial values."""
+import numpy as np
+import pytest
+from scipy.constants import h as C_h, e as C_e, epsilon_0, physical_constants
+
+import arc_b200
+
+
+def _fake_value(key, power):
+    return float(np.sin(sum((i + 1) * 1.37 * float(k) for i, k in enumerate(key[:6])) + power) * 100.0 + 3.0)
+
+
+def _patch(atom):
+    calls = []
+
+    def compute(keys, powers, s=0.5):
+        calls.append(len(keys))
+        return [_fake_value(k, p) for k, p in zip(keys, powers)]
+    atom._compute_elements = compute
+    atom._compute_calls = calls
+    return atom
+
+
+STARK_CASES = [
+    ("Rubidium", (28, 0, 0.5, 0.5, 26, 30, 8), {}),
+    ("Rubidium", (6, 0, 0.5, 0.5, 4, 9, 5), {}),                       # reaches below groundStateN
+    ("Caesium", (40, 2, 2.5, 1.5, 37, 43, 9), {"Bz": 1e-3}),
+    ("Strontium88", (55, 0, 0, 0, 53, 57, 10), {"s": 0}),
+    ("Strontium88", (55, 0, 1, 0, 53, 57, 10), {"s": 1}),
+    ("Potassium", (5, 1, 1.5, 0.5, 3, 7, 3), {}),                       # literature dipole elements
+]
+
+
+@pytest.mark.parametrize("atomname,args,kw", STARK_CASES)
+def test_stark_matrices_equal_per_element_path(atomname, args, kw):
+    atom = _patch(getattr(arc_b200, atomname)())
+    calc = arc_b200.StarkMap(atom)
+    calc.defineBasis(*args, **kw)
+    assert len(atom._compute_calls) <= 1                 # one batch for the whole table
+    s = kw.get("s", 0.5)
+    ref = _patch(getattr(arc_b200, atomname)())
+    chk = arc_b200.StarkMap(ref)
+    st = calc.basisStates
+    N = len(st)
+    mat2 = np.zeros((N, N))
+    for i in range(N):
+        for j in range(i + 1, N):
+            c = chk._eFieldCouplingDivE(st[i][0], st[i][1], st[i][2], st[i][3],
+                                        st[j][0], st[j][1], st[j][2], st[j][3], s=s) * 1.0e-9 / C_h
+            mat2[i, j] = mat2[j, i] = c
+    assert np.count_nonzero(mat2) > 0
+    assert np.array_equal(calc.mat2, mat2)
+    assert atom._dipole == ref._dipole
+    for i in range(N):
+        e = (ref.getEnergy(st[i][0], st[i][1], st[i][2], s=s) * C_e / C_h * 1e-9
+             + ref.getZeemanEnergyShift(st[i][1], st[i][2], st[i][3], kw.get("Bz", 0), s=s) / C_h * 1.0e-9)
+        assert calc.mat1[i, i] == e
+
+
+def test_shirley_couplings_equal_per_element_path():
+    atom = _patch(arc_b200.Rubidium85())
+    calc = arc_b200.ShirleyMethod(atom)
+    calc.defineBasis(40, 2, 2.5, 0.5, 0, 37, 43, 8)
+    ref = _patch(arc_b200.Rubidium85())
+    chk = arc_b200.ShirleyMethod(ref)
+    st = calc.basisStates
+    N = len(st)
+    V = np.zeros((N, N))
+    for i in range(N):
+        for j in range(i + 1, N):
+            # calculations_atom_single.py:3641-3660: both angular factors at the target's mj
+            c = 0.5 * chk._eFieldCouplingDivE(st[i][0], st[i][1], st[i][2], calc.mj,
+                                              st[j][0], st[j][1], st[j][2], calc.mj, s=0.5) / C_h
+            V[i, j] = V[j, i] = c
+    assert np.count_nonzero(V) > 0
+    assert np.array_equal(calc.V, V)
+
+
+PAIR_CASES = [
+    (lambda: (arc_b200.Rubidium(), None), (45, 0, .5, 45, 0, .5, .5, .5), {}, (0., 0., 2, 3, 15e9), {}),
+    (lambda: (arc_b200.Caesium(), None), (35, 2, 1.5, 36, 0, 0.5, 0.5, 0.5), {"interactionsUpTo": 2},
+     (0.7, 0., 1, 3, 6e9), {"Bz": 2e-4}),
+    (lambda: (arc_b200.Rubidium(), arc_b200.Caesium()), (45, 0, .5, 46, 1, 1.5, .5, .5), {}, (0., 0., 2, 3, 15e9), {}),
+    (lambda: (arc_b200.Strontium88(), None), (45, 0, 1, 45, 0, 1, 1, 1), {"s": 1, "interactionsUpTo": 2},
+     (0.3, 0., 1, 2, 10e9), {}),
+]
+
+
+@pytest.mark.parametrize("atoms,state,ckw,args,kw", PAIR_CASES)
+def test_pair_channel_couplings_equal_per_element_path(atoms, state, ckw, args, kw):
+    a1, a2 = atoms()
+    _patch(a1)
+    if a2 is not None:
+        _patch(a2)
+        ckw = dict(ckw, atom2=a2)
+    calc = arc_b200.PairStateInteractions(a1, *state, **ckw)
+    calc.defineBasis(*args, **kw)
+    r1, r2 = atoms()
+    _patch(r1)
+    r2 = r1 if r2 is None else _patch(r2)
+    a0 = physical_constants["Bohr radius"][0]
+    nch, found = len(calc.channel), 0
+    for o, cm in enumerate(calc.coupling):
+        cm = cm.tocoo()
+        assert len(cm.data) == 0 or (cm.row < cm.col).all()
+        for i, j, v in zip(cm.row, cm.col, cm.data):
+            ci, cj = calc.channel[i], calc.channel[j]
+            x1 = r1.getRadialCoupling(ci[0], ci[1], ci[2], cj[0], cj[1], cj[2], s=calc.s1)
+            x2 = r2.getRadialCoupling(ci[3], ci[4], ci[5], cj[3], cj[4], cj[5], s=calc.s2)
+            want = (C_e ** 2 / (4.0 * np.pi * epsilon_0) * x1 * x2 * a0 ** (o + 2)) / C_h * 1.0e-9
+            assert v == want
+            found += 1
+    assert found > 0 and nch > 1
+    assert a1._dipole == r1._dipole and a1._quadrupole == r1._quadrupole
+
+
+def test_radial_elements_vector_api():
+    atom = _patch(arc_b200.Rubidium())
+    rows = [(30, 0, .5, 30, 1, 1.5), (30, 1, 1.5, 30, 0, .5), (30, 0, .5, 31, 2, 1.5), (31, 1, .5, 30, 0, .5),
+            (30, 0, .5, 30, 1, 1.5), (5, 0, .5, 5, 1, .5)]
+    v = atom.radial_elements(rows, 1)
+    assert atom._compute_calls == [2]                                  # two distinct new elements, one batch
+    assert v[0] == v[1] == v[4] == atom.getRadialMatrixElement(30, 0, .5, 30, 1, 1.5)
+    assert v[2] == 0                                                   # dl = 2: forbidden
+    assert v[3] == atom.getRadialMatrixElement(30, 0, .5, 31, 1, .5)
+    assert v[5] == atom._lit[(5, 0, 1, 5, 1, 1)][0]                    # literature value wins
+    assert atom.radial_elements(rows, 1, useLiterature=False)[5] == atom._dipole[(5, 0, 1, 5, 1, 1)]
+    q = atom.radial_elements(rows, 2)
+    assert q[2] == atom.getQuadrupoleMatrixElement(30, 0, .5, 31, 2, 1.5) != 0
+    assert atom.radial_elements([], 1).shape == (0,)
+    assert atom.precompute_radial(dipole_pairs=rows) == 0              # everything memoised already
+    assert atom.precompute_radial(dipole_pairs=np.array([(40, 0, .5, 40, 1, .5)]),
+                                  quadrupole_pairs=[(40, 0, .5, 41, 2, 1.5)]) == 2
+    sr = _patch(arc_b200.Strontium88())
+    with pytest.raises(ValueError):
+        sr.radial_elements([(50, 0, 0, 50, 1, 1)], 1)
+    d = sr.radial_elements([(50, 0, 0, 50, 1, 1), (50, 1, 1, 50, 0, 0), (50, 0, 0, 50, 2, 2)], 1, s=0)
+    assert d[0] == d[1] == sr.getRadialMatrixElement(50, 0, 0, 50, 1, 1, s=0) and d[2] == 0
