@@ -62,7 +62,7 @@ def build_lib(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared"] + NVCC_FLAGS[:2] + ["-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

@@ -85,6 +85,7 @@ extern "C" int arcb200_semiclassical_table(int device, void *stream, int64_t n,
     if (n <= 0) return 0;
     if (kind != 1 && kind != 2) { arcb200_set_error("kind must be 1 or 2"); return -1; }
     if (nq <= 0 || (nq & 31)) { arcb200_set_error("nq must be a positive multiple of 32"); return -1; }
+    ARCB200_REQUIRE(d_in && d_quad && d_out, "semiclassical_table: null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     const int64_t grid = (n + 3) / 4;
     semiclassical_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(n, d_in, kind, d_quad, nq, d_out);

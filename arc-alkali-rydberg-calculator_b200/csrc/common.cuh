@@ -19,6 +19,16 @@ void arcb200_set_error(const char *fmt, ...);
         }                                                                          \
     } while (0)
 
+// argument validation at the C-ABI: checked on the host before any CUDA call, so a bad call
+// returns -1 with a message instead of hanging (batch = 0) or faulting on the device
+#define ARCB200_REQUIRE(cond, ...)                                                 \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            arcb200_set_error(__VA_ARGS__);                                        \
+            return -1;                                                             \
+        }                                                                          \
+    } while (0)
+
 #define ARCB200_LAUNCH_CHECK(name)                                                 \
     do {                                                                           \
         cudaError_t _e = cudaGetLastError();                                       \

@@ -413,6 +413,7 @@ extern "C" int arcb200_scatter_coo(int device, void *stream, int32_t N, int64_t 
                                    const double *d_vals, double *d_dense)
 {
     if (nnz <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1 && d_rows && d_cols && d_vals && d_dense, "scatter_coo: N < 1 or null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     scatter_coo_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(N, nnz, d_rows, d_cols, d_vals, d_dense);
     ARCB200_LAUNCH_CHECK("scatter_coo_kernel");
@@ -428,6 +429,11 @@ static int stark_sweep_impl(int device, void *stream, int32_t N, const double *d
 {
     if (h_launches) *h_launches = 0;
     if (nF <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1, "stark sweep: N = %d < 1", N);
+    ARCB200_REQUIRE(batch >= 1 && batch <= 65535, "stark sweep: batch = %d outside [1, 65535]", batch);
+    ARCB200_REQUIRE(d_h0diag && d_V && d_F && d_y && d_hl && d_work, "stark sweep: null operator, field, result or workspace pointer");
+    ARCB200_REQUIRE(idx0 >= 0 && idx0 < N, "stark sweep: tracked state index %d outside [0, %d)", idx0, N);
+    ARCB200_REQUIRE(topk >= 0 && (topk == 0 || (d_comp_c && d_comp_i)), "stark sweep: topk < 0 or null composition arrays");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -482,6 +488,7 @@ extern "C" int arcb200_floquet_sweep(int device, void *stream, int32_t N, int32_
                                      int32_t *h_launches)
 {
     if (dim0 <= 0 || N % dim0 != 0) { arcb200_set_error("floquet_sweep: N must be a multiple of dim0"); return -1; }
+    ARCB200_REQUIRE(nF <= 0 || d_tprob, "floquet_sweep: null transition-probability array");
     return stark_sweep_impl(device, stream, N, d_h0diag, d_B, nF, d_F, idx0, nullptr, 0, 2.0, d_y,
                             d_hl, nullptr, nullptr, d_work, wbytes, batch, dim0, d_tprob, h_launches);
 }
@@ -496,7 +503,13 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
 {
     if (h_launches) *h_launches = 0;
     if (nR <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1, "pair sweep: N = %d < 1", N);
     if (k < 1 || k > N) { arcb200_set_error("k must be in [1, N]"); return -1; }
+    ARCB200_REQUIRE(batch >= 1 && batch <= 65535, "pair sweep: batch = %d outside [1, 65535]", batch);
+    ARCB200_REQUIRE(norders >= 0 && (norders == 0 || d_M), "pair sweep: norders < 0 or null operator table");
+    ARCB200_REQUIRE(d_h0diag && d_R && d_y && d_hl && d_work, "pair sweep: null operator, distance, result or workspace pointer");
+    ARCB200_REQUIRE(opi >= 0 && opi < N, "pair sweep: tracked state index %d outside [0, %d)", opi, N);
+    ARCB200_REQUIRE(topk >= 0 && (topk == 0 || (d_comp_c && d_comp_i)), "pair sweep: topk < 0 or null composition arrays");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, k);
@@ -594,6 +607,8 @@ extern "C" int arcb200_syevd_batched(int device, void *stream, int32_t N, int32_
 {
     if (h_launches) *h_launches = 0;
     if (batch <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1 && batch <= 65535, "syevd_batched: N < 1 or batch > 65535");
+    ARCB200_REQUIRE(d_A && d_w && d_Z && d_work, "syevd_batched: null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -629,6 +644,9 @@ extern "C" int arcb200_sytrd_batched(int device, void *stream, int32_t N, int32_
                                      void *d_work, int64_t wbytes, int32_t cluster, int32_t *h_launches)
 {
     if (h_launches) *h_launches = 0;
+    if (batch <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1 && batch <= 65535, "sytrd_batched: N < 1 or batch > 65535");
+    ARCB200_REQUIRE(d_A && d_d && d_e && d_work, "sytrd_batched: null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -669,6 +687,9 @@ extern "C" int arcb200_sy2sb_batched(int device, void *stream, int32_t N, int32_
                                      int64_t wbytes, int32_t *h_launches)
 {
     if (h_launches) *h_launches = 0;
+    if (batch <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1 && batch <= 65535, "sy2sb_batched: N < 1 or batch > 65535");
+    ARCB200_REQUIRE(d_A && d_band && d_work, "sy2sb_batched: null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);
@@ -690,6 +711,9 @@ extern "C" int arcb200_stedc_batched(int device, void *stream, int32_t N, int32_
                                      double *d_Q, void *d_work, int64_t wbytes, int32_t *h_launches)
 {
     if (h_launches) *h_launches = 0;
+    if (batch <= 0) return 0;
+    ARCB200_REQUIRE(N >= 1 && batch <= 65535, "stedc_batched: N < 1 or batch > 65535");
+    ARCB200_REQUIRE(d_d && d_e && d_w && d_Q && d_work, "stedc_batched: null pointer");
     ARCB200_CUDA_CHECK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const EigLayout L = eig_layout(N, N);

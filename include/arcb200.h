@@ -9,8 +9,10 @@
  *     result buffers and never frees caller memory;
  *   - `device` is the CUDA ordinal, `stream` a cudaStream_t passed as void*
  *     (NULL = legacy default stream);
- *   - return value 0 = success, negative = error; arcb200_last_error() returns a
- *     thread-local message.  Entry points that launch a variable number of kernels report
+ *   - return value 0 = success, negative = error (-1 invalid argument or failed CUDA API call,
+ *     -2 kernel launch failure, -3 not an sm_100 device); arcb200_last_error() returns a
+ *     thread-local message.  Sizes, index ranges and required pointers are validated on the
+ *     host before the first CUDA call (tests/test_abi.py), so a bad call never hangs or faults.  Entry points that launch a variable number of kernels report
  *     the count through a trailing `int32_t *h_launches` (host pointer, may be NULL);
  *     per-item failures come back in device status arrays (d_status), never as aborts.  Nothing calls exit()/abort() (the reference's C
  *     extension returns NULL without setting an exception, arc_c_extensions.c:145,200);
