@@ -237,7 +237,9 @@ def bench_c3(args, rank, world):
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t1) * 1e3), world)
     e2e_value = npts * world * args.steps / (ms_e2e * 1e-3)
     batch = sweep._pick_batch(N, npts, k, torch.cuda.current_device())
-    return {"value": value, "ms": ms, "e2e_value": e2e_value, "ms_e2e": ms_e2e, "h2d": h2d, "d2h": d2h,
+    from arc_b200 import _lib
+    work_bytes = int(_lib.load().arcb200_sweep_workspace_bytes(N, batch, k))
+    return {"value": value, "work_bytes": work_bytes, "ms": ms, "e2e_value": e2e_value, "ms_e2e": ms_e2e, "h2d": h2d, "d2h": d2h,
             "launches": launches[0], "clocks": clk.summary(), "N": N, "k": k,
             "t_defineBasis_s": t_define, "batch": batch, "calc": calc, "R": myR}
 
@@ -437,9 +439,10 @@ def cpu_baseline_c3(calc, nR=4):
     (calculations_atom_pairstate.py:3425-3450) via the oracle, on a bounded sample, one core."""
     from oracle import oracle
     R = np.linspace(1.0, 10.0, 1000)[:: max(1, 1000 // max(nR, 1))][:nR]
-    t0 = time.perf_counter()
-    oracle.pair_diagonalise(calc.matDiagonal, calc.matR, R, 250, calc.originalPairStateIndex)
-    dt = time.perf_counter() - t0
+    with _one_thread():
+        t0 = time.perf_counter()
+        oracle.pair_diagonalise(calc.matDiagonal, calc.matR, R, 250, calc.originalPairStateIndex)
+        dt = time.perf_counter() - t0
     return len(R) / dt, dt
 
 
@@ -762,7 +765,7 @@ def main():
     v, dt = cpu_baseline_c3(calc, nR=args.cpu_pair_points)
     cpu = {"value": v, "unit": "solves/s", "cores": 1, "kind": "port",
            "sample": "%d of the R points, scipy.sparse.linalg.eigsh(k=250, sigma=0, tol=1e-6) per point "
-                     "(the reference's call, calculations_atom_pairstate.py:3444), default BLAS threads"
+                     "(the reference's call, calculations_atom_pairstate.py:3444), one BLAS thread"
                      % args.cpu_pair_points,
            "host_cores": os.cpu_count(), "cpu_model": cpu_model()}
     sub = {}
@@ -809,7 +812,7 @@ def main():
         "data": "synthetic (Rb 60S+60S pair Hamiltonian built from quantum defects by our own defineBasis; no dataset)",
         "config": {"workload": C3_WORKLOAD,
                    "points_per_step": args.points, "batch_in_flight": r["batch"],
-                   "l2": "inputs larger than L2 (batch workspace %.1f GB)" % (r["batch"] * 4 * (r["N"] ** 2) * 8 / 1e9),
+                   "l2": "inputs larger than L2 (batch workspace %.1f GB)" % (r["work_bytes"] / 1e9),
                    "parallelism": "sweep points sharded, %d rank(s), no data-path collective" % world},
         "e2e": {"value": r["e2e_value"], "unit": "solves/s", "h2d_bytes_per_step": r["h2d"],
                 "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms_e2e"] / args.steps,
