@@ -715,50 +715,63 @@ class PairStateInteractions:
         trivial = wgd.trivial
         self.matR = []
         self._matR_coo = []
+        index64 = index                                     # int64 copy of self.index
+        nstates_ch = np.diff(index64)
+        # the angular block and its sparsity pattern depend on the eight (l, j) numbers only (the m
+        # sub-levels kept per channel follow from j1, j2): channels are classed by (l1, j1, l2, j2),
+        # one block per pair of classes, and all coupled channel pairs of a class pair are expanded
+        # into matrix entries in one numpy step
+        lj = np.array([[ch[1], ch[2], ch[4], ch[5]] for ch in self.channel], dtype=np.float64).reshape(nch, 4)
+        ljc, cls = (np.unique(lj, axis=0, return_inverse=True) if nch else (lj, np.zeros(0, dtype=np.int64)))
+        cls = np.asarray(cls).ravel()
+        first_of = np.zeros(len(ljc), dtype=np.int64)
+        first_of[cls[::-1]] = np.arange(nch)[::-1]          # a representative channel per class
         blkcache = {}
+
+        def block(ci, cj):
+            """(rows within channel j, columns within channel i, values) of the angular block between the
+            channel classes ci -> cj, entries with |value| <= 1e-5 dropped (pair:3198-3217); () if empty."""
+            ii, jjc = int(first_of[ci]), int(first_of[cj])
+            chi, chj = self.channel[ii], self.channel[jjc]
+            af = self._angular_factors(chi[1], chi[2], chi[4], chi[5], chj[1], chj[2], chj[4], chj[5])
+            if af is None or af[0] == 0.0:
+                return ()
+            elem, terms = af
+            if trivial:
+                B = elem * sum(f * _kron(A, Bm) for f, A, Bm in terms)
+            else:
+                D1, D2 = wgd.get(chi[2]), wgd.get(chi[5])
+                D3, D4 = wgd.get(chj[2]), wgd.get(chj[5])
+                B = elem * sum(f * _kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
+                               for f, A, Bm in terms)
+                B = B.real
+            blk = B[np.ix_(prod_idx[jjc], prod_idx[ii])]     # rows: j states, cols: i states
+            jr, ic = np.nonzero(np.abs(blk) > 1.0e-5)
+            return (jr, ic, blk[jr, ic]) if len(jr) else ()
+
         for c in self.coupling:
             rows, cols, vals = [], [], []
             c = c.tocsr()
-            for ii in range(nch):
-                chi = self.channel[ii]
-                if self.index[ii] == self.index[ii + 1]:
+            ci_all = np.repeat(np.arange(nch), np.diff(c.indptr))
+            cj_all = np.asarray(c.indices, dtype=np.int64)
+            keep = (nstates_ch[ci_all] > 0) & (nstates_ch[cj_all] > 0)
+            ci_all, cj_all, rho_all = ci_all[keep], cj_all[keep], np.asarray(c.data)[keep]
+            code = cls[ci_all] * len(ljc) + cls[cj_all]
+            order = np.argsort(code, kind="stable")
+            bounds = np.flatnonzero(np.diff(code[order])) + 1
+            for grp in np.split(order, bounds) if len(order) else []:
+                k0 = int(code[grp[0]])
+                hit = blkcache.get(k0)
+                if hit is None:
+                    hit = blkcache[k0] = block(k0 // len(ljc), k0 % len(ljc))
+                if not hit:
                     continue
-                for p_ in range(c.indptr[ii], c.indptr[ii + 1]):
-                    jjc = c.indices[p_]
-                    if self.index[jjc] == self.index[jjc + 1]:
-                        continue
-                    rho = c.data[p_]
-                    chj = self.channel[jjc]
-                    # the angular block and its sparsity pattern depend on the eight (l, j) numbers
-                    # only (the m sub-levels kept per channel follow from j1, j2): built once per key
-                    akey = (chi[1], chi[2], chi[4], chi[5], chj[1], chj[2], chj[4], chj[5])
-                    hit = blkcache.get(akey)
-                    if hit is None:
-                        af = self._angular_factors(*akey)
-                        if af is None or af[0] == 0.0:
-                            hit = ()
-                        else:
-                            elem, terms = af
-                            if trivial:
-                                B = elem * sum(f * _kron(A, Bm) for f, A, Bm in terms)
-                            else:
-                                D1, D2 = wgd.get(chi[2]), wgd.get(chi[5])
-                                D3, D4 = wgd.get(chj[2]), wgd.get(chj[5])
-                                B = elem * sum(f * _kron(D3 @ A @ D1.conj().T, D4 @ Bm @ D2.conj().T)
-                                               for f, A, Bm in terms)
-                                B = B.real
-                            blk = B[np.ix_(prod_idx[jjc], prod_idx[ii])]     # rows: j states, cols: i states
-                            jr, ic = np.nonzero(np.abs(blk) > 1.0e-5)
-                            hit = (jr, ic, blk[jr, ic]) if len(jr) else ()
-                        blkcache[akey] = hit
-                    if not hit:
-                        continue
-                    jr, ic, bv = hit
-                    v = rho * bv
-                    gi = self.index[ii] + ic
-                    gj = self.index[jjc] + jr
-                    rows.append(gi); cols.append(gj); vals.append(v)
-                    rows.append(gj); cols.append(gi); vals.append(v)
+                jr, ic, bv = hit
+                v = (rho_all[grp][:, None] * bv[None, :]).ravel()
+                gi = (index64[ci_all[grp]][:, None] + ic[None, :]).ravel()
+                gj = (index64[cj_all[grp]][:, None] + jr[None, :]).ravel()
+                rows.append(gi); cols.append(gj); vals.append(v)
+                rows.append(gj); cols.append(gi); vals.append(v)
             if rows:
                 rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
             else:

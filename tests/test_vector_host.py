@@ -142,3 +142,51 @@ def test_radial_elements_vector_api():
         sr.radial_elements([(50, 0, 0, 50, 1, 1)], 1)
     d = sr.radial_elements([(50, 0, 0, 50, 1, 1), (50, 1, 1, 50, 0, 0), (50, 0, 0, 50, 2, 2)], 1, s=0)
     assert d[0] == d[1] == sr.getRadialMatrixElement(50, 0, 0, 50, 1, 1, s=0) and d[2] == 0
+
+
+@pytest.mark.parametrize("atomname,state,upto,theta,args,kw", [
+    ("Rubidium", (45, 0, .5, 45, 0, .5, .5, .5), 1, 0.0, (2, 3, 15e9), {}),
+    ("Caesium", (35, 2, 1.5, 36, 0, 0.5, 0.5, 0.5), 2, 0.7, (1, 3, 6e9), {"Bz": 2e-4})])
+def test_matR_blocks_equal_the_closed_form_per_channel_pair(atomname, state, upto, theta, args, kw):
+    """matR is expanded class pair by class pair; here it is rebuilt channel pair by channel pair
+    from SURVEY a16': matR[o][rows of j, cols of i] = rho * Re[(D(j1') x D(j2')) d (D(j1) x D(j2))^+],
+    entries with |angular| <= 1e-5 dropped, Hermitian mirror added (pair:3116-3217)."""
+    from arc_b200 import WignerDmatrix
+    atom = _patch(getattr(arc_b200, atomname)())
+    calc = arc_b200.PairStateInteractions(atom, *state, interactionsUpTo=upto)
+    calc.defineBasis(theta, 0., *args, **kw)
+    N, index = len(calc.basisStates), calc.index.astype(np.int64)
+    wgd = WignerDmatrix(theta, 0.)
+
+    def prod_idx(ch_i):
+        out = []
+        for b in calc.basisStates[index[ch_i]:index[ch_i + 1]]:
+            out.append(round(b[3] + b[2]) * round(2 * b[6] + 1) + round(b[7] + b[6]))
+        return np.array(out, dtype=np.int64)
+    seen = 0
+    for o, cm in enumerate(calc.coupling):
+        want = np.zeros((N, N))
+        cm = cm.tocoo()
+        for i, j, rho in zip(cm.row, cm.col, cm.data):
+            chi, chj = calc.channel[i], calc.channel[j]
+            if index[i] == index[i + 1] or index[j] == index[j + 1]:
+                continue
+            d = calc._getAngularMatrix_M(chi[1], chi[2], chi[4], chi[5], chj[1], chj[2], chj[4], chj[5])
+            d = np.asarray(d.todense() if hasattr(d, "todense") else d)
+            if theta != 0.0:
+                d = (np.kron(wgd.get(chj[2]), wgd.get(chj[5])) @ d
+                     @ np.kron(wgd.get(chi[2]), wgd.get(chi[5])).conj().T).real
+            blk = d[np.ix_(prod_idx(j), prod_idx(i))]
+            blk = np.where(np.abs(blk) > 1.0e-5, blk, 0.0) * rho
+            want[index[j]:index[j + 1], index[i]:index[i + 1]] += blk
+            want[index[i]:index[i + 1], index[j]:index[j + 1]] += blk.T
+            seen += 1
+        got = calc.matR[o].toarray()
+        scale = max(np.abs(want).max(), 1e-300)
+        assert np.abs(got - want).max() <= 1e-13 * scale
+        # what is staged on the GPU (COO scatter) is the same matrix
+        r, c, v = calc._matR_coo[o]
+        dense = np.zeros((N, N))
+        dense[r, c] = v
+        assert np.array_equal(dense, got) and len(set(zip(r.tolist(), c.tolist()))) == len(r)
+    assert seen >= 20
