@@ -146,7 +146,7 @@ def test_radial_elements_vector_api():
 
 @pytest.mark.parametrize("atomname,state,upto,theta,args,kw", [
     ("Rubidium", (45, 0, .5, 45, 0, .5, .5, .5), 1, 0.0, (2, 3, 15e9), {}),
-    ("Caesium", (35, 2, 1.5, 36, 0, 0.5, 0.5, 0.5), 2, 0.7, (1, 3, 6e9), {"Bz": 2e-4})])
+    ("Caesium", (35, 2, 1.5, 36, 0, 0.5, 0.5, 0.5), 2, 0.7, (2, 3, 6e9), {"Bz": 2e-4})])
 def test_matR_blocks_equal_the_closed_form_per_channel_pair(atomname, state, upto, theta, args, kw):
     """matR is expanded class pair by class pair; here it is rebuilt channel pair by channel pair
     from SURVEY a16': matR[o][rows of j, cols of i] = rho * Re[(D(j1') x D(j2')) d (D(j1) x D(j2))^+],
