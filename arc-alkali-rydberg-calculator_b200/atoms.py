@@ -376,7 +376,7 @@ class AlkaliAtom:
             return out
         memo = self._dipole if power == 1 else self._quadrupole
         lit = self._lit if (power == 1 and useLiterature) else {}
-        missing = [k for k in keys if k not in memo and k not in lit]
+        missing = [k for k in dict.fromkeys(keys) if k not in memo and k not in lit]   # S may repeat a state
         if missing:
             memo.update(zip(missing, self._compute_elements(missing, [power] * len(missing), s)))
         if lit:
@@ -404,7 +404,7 @@ class AlkaliAtom:
                 continue
             _ok, keys, _inv = self._unique_elements(*self._index_states(P), power, s)
             lit = self._lit if (power == 1 and useLiterature) else {}
-            fresh.append([k for k in keys if k not in memo and k not in lit])
+            fresh.append([k for k in dict.fromkeys(keys) if k not in memo and k not in lit])
         nd, nq = len(fresh[0]), len(fresh[1])
         if nd + nq == 0:
             return 0
