@@ -106,3 +106,88 @@ def test_radial_table_sharded_allgather_gloo_world2():
     assert sorted(o[2] for o in outs) == [500, 501]          # each rank computed only its shard
     for rank, full, _n in outs:
         assert np.array_equal(full, want)
+
+
+class _FakeRadialBatch:
+    """CPU stand-in for radial.RadialBatch (the real one runs the Numerov kernel): element values
+    are a deterministic function of the two state records and the power, so a sharded table has
+    to equal the unsharded one entry by entry."""
+    kernel_launches = 2
+    shard_sizes = []
+
+    def __init__(self, states, normalise=True, device=None):
+        self.states = np.asarray(states)
+
+    def _values(self, rows):
+        rows = np.asarray(rows).reshape(-1, 3)
+        a, b = self.states[rows[:, 0]], self.states[rows[:, 1]]
+        v = np.sin(37.0 * a["stateEnergy"] * 1e3 + a["l"] + 2.0 * a["j"]) * np.cos(91.0 * b["stateEnergy"] * 1e3 + b["l"]) \
+            * (10.0 ** rows[:, 2]) + 3.0
+        return torch.as_tensor(v, dtype=torch.float64)
+
+    def integrals(self, rows):
+        return self._values(rows).numpy()
+
+    def integrals_sharded(self, rows, group="world"):
+        from arc_b200 import radial
+
+        def compute(shard):
+            _FakeRadialBatch.shard_sizes.append(len(shard))
+            return self._values(shard)
+        return radial.sharded_table(compute, np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 3), group)
+
+
+def _definebasis_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import arc_b200
+        from arc_b200 import radial
+        radial.RadialBatch = _FakeRadialBatch
+
+        def stark(group):
+            atom = arc_b200.Rubidium()
+            atom.radial_group = group
+            calc = arc_b200.StarkMap(atom)
+            calc.defineBasis(30, 0, 0.5, 0.5, 26, 34, 12)
+            return calc
+
+        def pair(group):
+            atom = arc_b200.Rubidium()
+            atom.radial_group = group
+            calc = arc_b200.PairStateInteractions(atom, 50, 0, .5, 50, 0, .5, .5, .5, interactionsUpTo=2)
+            calc.defineBasis(0., 0., 4, 4, 25e9)
+            return calc
+        _FakeRadialBatch.shard_sizes = []
+        s_sh, p_sh = stark(sweep.WORLD), pair(sweep.WORLD)          # collective: both ranks call them
+        sizes = list(_FakeRadialBatch.shard_sizes)
+        s_1, p_1 = stark(None), pair(None)                          # every rank on its own, no collective
+        ok = np.array_equal(s_sh.mat2, s_1.mat2) and s_sh.atom._dipole == s_1.atom._dipole
+        for a, b in zip(p_sh.matR, p_1.matR):
+            ok = ok and (abs(a - b)).nnz == 0 and a.nnz > 0
+        ok = ok and p_sh.atom1._quadrupole == p_1.atom1._quadrupole and len(p_1.atom1._quadrupole) > 0
+        q.put((rank, bool(ok), sizes, len(s_1.atom._dipole), len(p_1.atom1._dipole) + len(p_1.atom1._quadrupole)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_definebasis_with_sharded_radial_table_gloo_world2():
+    """atom.radial_group: StarkMap / PairStateInteractions.defineBasis on two ranks build the same
+    matrices as an unsharded run, each rank evaluating half of every radial table (>= 1024 new
+    elements) -- the host path the 2/4/8-GPU bench runs, with the Numerov kernel stubbed."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_definebasis_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, sizes, n_stark, n_pair in outs:
+        assert ok
+        assert n_stark >= 1024 and n_pair >= 1024
+        assert len(sizes) == 2                                       # one sharded table per defineBasis
+        assert abs(sizes[0] - n_stark / 2) <= 1 and abs(sizes[1] - n_pair / 2) <= 1
