@@ -702,6 +702,10 @@ def run_reference(args):
             pools[p].close()
     pool = pools[best]
     per = max(1, args.ref_points_per_proc)
+    # bounded sample: the K timed steps are projected from the swept rate and the points per worker are
+    # reduced until they fit --ref-max-seconds (the arm has to end within a few minutes for any K)
+    while per > 1 and args.steps * best * per / max(best_rate, 1e-9) > args.ref_max_seconds:
+        per -= 1
     nR = best * per
     for _ in range(min(args.warmup, 1)):
         one_pass(pool, best, per)
@@ -744,6 +748,8 @@ def main():
     ap.add_argument("--cpu-c5-points", type=int, default=1)
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-points-per-proc", type=int, default=2)
+    ap.add_argument("--ref-max-seconds", type=float, default=240.0,
+                    help="reference arm: projected wall time of the timed steps above which the sample shrinks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
