@@ -39,6 +39,26 @@ void arcb200_set_error(const char *fmt, ...);
         }                                                                          \
     } while (0)
 
+// Helper streams of the library (sub-batches of the band reduction, the opt-in half-batch pipeline): one pool
+// per device, created on first use and kept for the life of the process.  A host thread takes
+// ArcHelperGuard while it ENQUEUES work that touches the pool (the GPU work itself is asynchronous), so
+// concurrent callers on one device cannot interleave their event records / waits.
+struct ArcHelperStreams {
+    static constexpr int MAXS = 8;
+    cudaStream_t stream[MAXS];
+    cudaEvent_t ev[MAXS + 1];
+    cudaStream_t pipe_stream[2];
+    cudaEvent_t pipe_ev[3];
+};
+struct ArcHelperGuard {
+    ArcHelperGuard();
+    ~ArcHelperGuard();
+    ArcHelperGuard(const ArcHelperGuard &) = delete;
+    ArcHelperGuard &operator=(const ArcHelperGuard &) = delete;
+    // pool of `device` (nullptr after arcb200_set_error if a stream or event cannot be created)
+    ArcHelperStreams *pool(int device);
+};
+
 static __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

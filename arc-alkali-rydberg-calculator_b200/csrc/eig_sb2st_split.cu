@@ -268,12 +268,9 @@ static int launch_split(const ts::TsArgs &a, int nmat, cudaStream_t st)
 
 int eig_sb2st_split(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launches)
 {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     int pairs = 8;
     if (a.N <= 1024 && nmat > sms) pairs = 4;
     if (a.N <= 512 && nmat > 2 * sms) pairs = 2;

@@ -555,17 +555,14 @@ extern "C" int arcb200_pair_sweep(int device, void *stream, int32_t N, const dou
     // two streams lets the one-CTA-per-matrix stages of a chunk run beside the band reduction of the next -- but
     // those stages take as long for 37 matrices as for 74 (latency bound per matrix), so the sweep got slower:
     // C5 74 points 5.94 -> 7.13 s, C3 125 points 281 -> 283 ms, 74 points 186 -> 217 ms (tools/ab_pipeline.py).
-    static cudaStream_t pstream[2];
-    static cudaEvent_t pev[3];
-    static int pdev = -1;
     const char *epl = getenv("ARCB200_PIPELINE");
     const bool pipe = epl && epl[0] == '1' && L.two_stage && !d_overlap && batch >= 2;
     if (pipe) {
-        if (pdev != device) {
-            for (int i = 0; i < 2; ++i) ARCB200_CUDA_CHECK(cudaStreamCreateWithFlags(&pstream[i], cudaStreamNonBlocking));
-            for (int i = 0; i < 3; ++i) ARCB200_CUDA_CHECK(cudaEventCreateWithFlags(&pev[i], cudaEventDisableTiming));
-            pdev = device;
-        }
+        ArcHelperGuard guard;          // held while the chunks are enqueued on the device's pipeline streams
+        ArcHelperStreams *hp = guard.pool(device);
+        if (!hp) return -1;
+        cudaStream_t *pstream = hp->pipe_stream;
+        cudaEvent_t *pev = hp->pipe_ev;
         ARCB200_CUDA_CHECK(cudaEventRecord(pev[2], st));
         for (int i = 0; i < 2; ++i) ARCB200_CUDA_CHECK(cudaStreamWaitEvent(pstream[i], pev[2], 0));
         const int half = (batch + 1) / 2;

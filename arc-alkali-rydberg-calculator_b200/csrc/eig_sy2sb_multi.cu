@@ -141,18 +141,14 @@ int eig_sy2sb_multi(const ts::TsArgs &a, int nmat, cudaStream_t st, int *launche
     // the other sub-batches (tools/ab_multi.py, 1 / 2 / 4 / 8 streams: 2363 x296 251.2 / 239.8 / 239.7 / 236.9 ms,
     // 2363 x125 119.5 / 114.6 / 109.4 / 109.0, 651 x286 10.7 / 9.9 / 9.7 / 9.7, 410 x300 5.4 / 4.3 / 3.9 / 3.8).
     // ARCB200_SY2SB_STREAMS = 1..8 overrides the choice below.
-    constexpr int MAXS = 8;
-    static cudaStream_t istream[MAXS];
-    static cudaEvent_t iev[MAXS + 1];
-    static int idev = -1;
+    constexpr int MAXS = ArcHelperStreams::MAXS;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (idev != dev) {
-        // (re)create for this device; a process drives one device (one rank per GPU)
-        for (int s = 0; s < MAXS; ++s) ARCB200_CUDA_CHECK(cudaStreamCreateWithFlags(&istream[s], cudaStreamNonBlocking));
-        for (int s = 0; s <= MAXS; ++s) ARCB200_CUDA_CHECK(cudaEventCreateWithFlags(&iev[s], cudaEventDisableTiming));
-        idev = dev;
-    }
+    ArcHelperGuard guard;              // held while this call enqueues on the device's helper streams
+    ArcHelperStreams *hp = guard.pool(dev);
+    if (!hp) return -1;
+    cudaStream_t *istream = hp->stream;
+    cudaEvent_t *iev = hp->ev;
     // (eight streams only pay for large matrices: 651 x286 and 410 x300 are as fast with four and half the launches)
     int ns = (nmat >= 256 && a.N > 1024) ? 8 : (nmat >= 64 ? 4 : (nmat >= 16 ? 2 : 1));
     const char *esn = getenv("ARCB200_SY2SB_STREAMS");

@@ -16,8 +16,11 @@
  *     the count through a trailing `int32_t *h_launches` (host pointer, may be NULL);
  *     per-item failures come back in device status arrays (d_status), never as aborts.  Nothing calls exit()/abort() (the reference's C
  *     extension returns NULL without setting an exception, arc_c_extensions.c:145,200);
- *   - re-entrant per (device, stream); no file-scope state (the reference keeps all
- *     integrator state in globals, arc_c_extensions.c:11-24,57-67).
+ *   - re-entrant per (device, stream): no integrator or solver state outlives a call (the
+ *     reference keeps all integrator state in globals, arc_c_extensions.c:11-24,57-67).  The only
+ *     process-wide objects are one pool of helper streams / events per device (sub-batches of the
+ *     band reduction), created on first use; a host thread holds the pool's mutex while it enqueues,
+ *     so concurrent callers on one device are safe (their sub-batches queue behind each other).
  */
 #ifndef ARCB200_H
 #define ARCB200_H
