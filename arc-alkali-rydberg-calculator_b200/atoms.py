@@ -255,6 +255,7 @@ class AlkaliAtom:
                                  stateEnergy, self.alphaC, self.alpha, self.Z, *p, mu)
         rb = _radial.RadialBatch(np.array([rec]), normalise=True, device=self.device)
         self.gpu_kernel_launches += rb.kernel_launches
+        rb.raise_on_failure()
         return rb.wavefunction(0)
 
     # --------------------------------------------------------- radial matrix elements
@@ -335,6 +336,7 @@ class AlkaliAtom:
         pair_rows = np.empty((len(keys), 3), dtype=np.int32)
         pair_rows[:, 0], pair_rows[:, 1], pair_rows[:, 2] = ia, ib, powers
         rb = _radial.RadialBatch(np.array(states), normalise=True, device=self.device)
+        rb.raise_on_failure()          # a state without a usable wavefunction: error, not a silent bad table
         if getattr(self, "radial_group", None) is not None and len(keys) >= 1024:
             # collective: every rank of the group builds the same table
             vals = rb.integrals_sharded(pair_rows, self.radial_group).cpu().numpy()

@@ -22,6 +22,7 @@ def NumerovWavefunction(innerLimit, outerLimit, step, init1, init2, l, s, j,
     rb = _radial.RadialBatch(np.array([rec]), normalise=False)
     if int(rb.lengths[0]) < 3 or int(rb.divergence_points()[0]) < 0:
         raise RuntimeError("Numerov integration failed (grid too short)")
+    rb.raise_on_failure()
     r, psi = rb.wavefunction(0)
     return np.ascontiguousarray(np.stack([psi, r]))
 
