@@ -18,6 +18,22 @@ def _free_port():
     return p
 
 
+def _collect(procs, q, timeout):
+    """One result per process; a worker that died without reporting fails the test at once
+    (instead of after the queue timeout)."""
+    import queue
+    import time
+    outs, t0 = [], time.time()
+    while len(outs) < len(procs):
+        try:
+            outs.append(q.get(timeout=1.0))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            assert not dead, "worker exited with %r before reporting" % dead
+            assert time.time() - t0 < timeout, "timed out waiting for the workers"
+    return outs
+
+
 def _worker(rank, world, port, npoints, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -44,7 +60,7 @@ def _run(npoints):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, npoints, q)) for r in range(2)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=120) for _ in procs]
+    outs = _collect(procs, q, 120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -97,7 +113,7 @@ def test_radial_table_sharded_allgather_gloo_world2():
     procs = [ctx.Process(target=_table_worker, args=(r, 2, port, npairs, q)) for r in range(2)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=120) for _ in procs]
+    outs = _collect(procs, q, 120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -124,6 +140,9 @@ class _FakeRadialBatch:
         v = np.sin(37.0 * a["stateEnergy"] * 1e3 + a["l"] + 2.0 * a["j"]) * np.cos(91.0 * b["stateEnergy"] * 1e3 + b["l"]) \
             * (10.0 ** rows[:, 2]) + 3.0
         return torch.as_tensor(v, dtype=torch.float64)
+
+    def raise_on_failure(self):
+        pass
 
     def integrals(self, rows):
         return self._values(rows).numpy()
@@ -182,7 +201,7 @@ def test_definebasis_with_sharded_radial_table_gloo_world2():
     procs = [ctx.Process(target=_definebasis_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=240) for _ in procs]
+    outs = _collect(procs, q, 240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
