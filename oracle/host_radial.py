@@ -53,3 +53,32 @@ def patch_atom_with_oracle(atom, procs=1):
             return pool.map(_element_worker, jobs, chunksize=max(1, len(jobs) // (8 * procs)))
     atom._compute_elements = compute_elements
     return atom
+
+
+def _semiclassical_worker(job):
+    kind, nu, nu1, l1, l2 = job
+    fn = oracle.semiclassical_dipole if kind == 1 else oracle.semiclassical_quadrupole
+    return fn(nu, nu1, l1, l2)
+
+
+def patch_divalent_with_oracle(atom, procs=1):
+    """Same for a DivalentAtom: its compute hook (semiclassical elements from the GPU Anger kernel)
+    is replaced by the oracle's mpmath restatement of alkali_atom_functions.py:2683-2802."""
+    import numpy as np
+
+    def compute_elements(keys, powers, s=None):
+        powers = np.asarray(powers)
+        jobs = [None] * len(keys)
+        for kind in (1, 2):
+            sel = np.flatnonzero(powers == kind)
+            if len(sel):
+                params = atom._semiclassical_params([keys[i] for i in sel], kind, s)
+                for i, p in zip(sel, params):
+                    jobs[i] = (kind, float(p[0]), float(p[1]), float(p[2]), float(p[3]))
+        if procs <= 1 or len(jobs) < 4 * procs:
+            return [_semiclassical_worker(j) for j in jobs]
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(_semiclassical_worker, jobs, chunksize=max(1, len(jobs) // (8 * procs)))
+    atom._compute_elements = compute_elements
+    return atom

@@ -114,6 +114,34 @@ def test_stark_basis_below_ground_state_matches_reference(gold_dir, name, cls):
     assert np.abs(calc.mat2 - m2).max() <= 1e-8 * np.abs(m2).max()
 
 
+@pytest.mark.parametrize("name,N", [("stark_c4_singlet_golden.npz", 651), ("stark_c4_triplet_golden.npz", 1932)])
+def test_stark_c4_full_size_host_logic(gold_dir, name, N):
+    """BASELINE configs[3] at its stated size on the CPU: Sr88 basis, `mat1`, `mat2` against the live
+    reference with the semiclassical radial elements from the oracle (mpmath Anger functions); the
+    GPU twin is tests/test_round2_gpu.py::test_c4_sr88_full_size_matches_reference."""
+    import arc_b200
+    from oracle.host_radial import patch_divalent_with_oracle
+    g = np.load(os.path.join(gold_dir, name))
+    calc = arc_b200.StarkMap(patch_divalent_with_oracle(arc_b200.Strontium88(), procs=min(8, os.cpu_count() or 1)))
+    a = g["args"]
+    calc.defineBasis(int(a[0]), int(a[1]), float(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]),
+                     s=float(g["s"]))
+    assert len(calc.basisStates) == N == len(g["basisStates"])
+    assert np.allclose(np.array(calc.basisStates), g["basisStates"])
+    assert calc.indexOfCoupledState == int(g["indexOfCoupledState"])
+    d = np.diag(calc.mat1)
+    assert np.abs(d - g["mat1_diag"]).max() <= 1e-12 * np.abs(d).max()
+    m2 = np.zeros((N, N))
+    m2[g["mat2_rows"], g["mat2_cols"]] = g["mat2_vals"]
+    # dipole-forbidden triplet pairs carry the reference's Clebsch-Gordan rounding noise instead of an
+    # exact zero (divalent_atom_functions.py:405): compared absolutely below 1e-13 of the scale
+    floor = 1e-13 * np.abs(m2).max()
+    nz = np.abs(m2) > floor
+    assert np.array_equal(np.abs(calc.mat2) > floor, nz)
+    assert np.abs(calc.mat2[nz] / m2[nz] - 1).max() <= 1e-10
+    assert np.abs(calc.mat2[~nz] - m2[~nz]).max() <= floor
+
+
 def test_composition_view_and_pickle():
     from arc_b200.stark import CompositionView
     c = np.array([[[0.9, -0.3, 0.0], [1.0, 0.0, 0.0]]])

@@ -107,6 +107,25 @@ def test_oracle_stark_matches_golden(gold_dir):
     np.testing.assert_allclose(hl, g["highlight"][[0, 6, 12]], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("name,pick", [("stark_c4_singlet_golden.npz", [0, 3, 7]), ("stark_c4_triplet_golden.npz", [5])])
+def test_oracle_stark_c4_matches_golden(gold_dir, name, pick):
+    """The oracle's sweep restatement on the Sr88 matrices of BASELINE configs[3] (many exactly equal
+    diagonal entries): eigenvalues against the live reference, highlight as sums over degenerate clusters."""
+    g = np.load(os.path.join(gold_dir, name))
+    N = len(g["mat1_diag"])
+    mat2 = np.zeros((N, N))
+    mat2[g["mat2_rows"], g["mat2_cols"]] = g["mat2_vals"]
+    y, hl, _ = oracle.stark_diagonalise(np.diag(g["mat1_diag"]), mat2, g["fields"][pick],
+                                        int(g["indexOfCoupledState"]), want_composition=False)
+    scale = np.abs(g["y"]).max()
+    assert np.abs(y - g["y"][pick]).max() <= 1e-9 * scale
+    for q, f in enumerate(pick):
+        edges = np.flatnonzero(np.diff(g["y"][f]) > 1e-7 * scale) + 1
+        A = np.add.reduceat(hl[q], np.r_[0, edges])
+        B = np.add.reduceat(g["highlight"][f], np.r_[0, edges])
+        assert np.abs(A - B).max() <= 1e-6
+
+
 def test_oracle_numerov_back_matches_live_reference(gold_dir):
     """Restatement of the pure-Python NumerovBack (aaf:3939-4063) against outputs of the live
     reference for analytic callables: bit-exact, including the divergence cut."""
