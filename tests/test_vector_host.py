@@ -190,3 +190,30 @@ def test_matR_blocks_equal_the_closed_form_per_channel_pair(atomname, state, upt
         dense[r, c] = v
         assert np.array_equal(dense, got) and len(set(zip(r.tolist(), c.tolist()))) == len(r)
     assert seen >= 20
+
+
+def test_unique_bounded_equals_numpy_unique():
+    from arc_b200.atoms import _unique_bounded
+    rng = np.random.default_rng(3)
+    for hi, m in ((5, 40), (1000, 300), (1 << 23, 50), (3, 1), (10 ** 12, 200)):
+        code = rng.integers(0, hi, size=m)
+        uc, rep, inv = _unique_bounded(code)
+        u2, _f2, i2 = np.unique(code, return_index=True, return_inverse=True)
+        assert np.array_equal(uc, u2) and np.array_equal(inv, i2.ravel())
+        assert np.array_equal(code[rep], uc)                      # a valid representative of every value
+    for empty in _unique_bounded(np.zeros(0, dtype=np.int64)):
+        assert len(empty) == 0
+
+
+def test_index_states_round_trip():
+    rng = np.random.default_rng(5)
+    n = rng.integers(4, 80, size=(200, 2))
+    l = np.minimum(rng.integers(0, 30, size=(200, 2)), n - 1)
+    j = l + rng.choice([-0.5, 0.5], size=(200, 2))
+    j = np.where(j < 0, 0.5, j)
+    P = np.stack([n[:, 0], l[:, 0], j[:, 0], n[:, 1], l[:, 1], j[:, 1]], axis=1).astype(np.float64)
+    S, ia, ib = arc_b200.AlkaliAtom._index_states(P)
+    assert np.array_equal(S[ia], P[:, 0:3]) and np.array_equal(S[ib], P[:, 3:6])
+    assert len(np.unique(S, axis=0)) == len(S)                    # every distinct state once
+    S0, a0, b0 = arc_b200.AlkaliAtom._index_states(np.zeros((0, 6)))
+    assert S0.shape == (0, 3) and len(a0) == len(b0) == 0
