@@ -17,7 +17,7 @@ import os
 from math import floor, sqrt
 
 import numpy as np
-from scipy.constants import physical_constants, m_e as C_m_e, h as C_h, e as C_e
+from scipy.constants import physical_constants, m_e as C_m_e
 
 from .wigner import CG
 from . import radial as _radial

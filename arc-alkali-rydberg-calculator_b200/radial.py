@@ -7,7 +7,6 @@ more kernel launch (one warp per pair).  Replaces the per-element call chain
 getRadialMatrixElement -> radialWavefunction x2 -> NumerovWavefunction -> trapezoid
 (alkali_atom_functions.py:978-1105, 503-625) of the reference.
 """
-import ctypes
 
 import numpy as np
 

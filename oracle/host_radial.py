@@ -4,7 +4,6 @@ Lets the `not gpu` tests exercise the host logic (basis enumeration, channel pre
 angular algebra, matrix assembly) of StarkMap / PairStateInteractions on a box with no
 GPU.  Test infrastructure only -- never imported by the product package.
 """
-import os
 
 from oracle import oracle
 
