@@ -690,14 +690,16 @@ def run_reference(args):
     if args.ref_procs:
         cands = [min(cores, args.ref_procs)]
     sweep_log, best, best_rate, pools = {}, None, -1.0, {}
-    for p in cands:
+    for p in cands:                                    # ascending
         pools[p] = ctx.Pool(p)
         one_pass(pools[p], p, 1)                       # spawn + first-touch warm-up
         rate, _ = one_pass(pools[p], p, 1)
         sweep_log[str(p)] = round(rate, 3)
         if rate > best_rate:
             best, best_rate = p, rate
-    for p in cands:
+        elif rate < 0.9 * best_rate:
+            break                                      # past the knee (memory-bound SuperLU solves): stop sweeping
+    for p in pools:
         if p != best:
             pools[p].close()
     pool = pools[best]
