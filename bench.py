@@ -49,6 +49,14 @@ L2_BYTES_PER_CLK = 6300.0          # B300_MICROARCH.md "TMA chip-throughput ~630
 
 
 # --------------------------------------------------------------------------- helpers
+def bench_config(points, world):
+    """`config` of the JSON line -- the same dict for this arm and for `--impl reference` (whose bounded
+    sample of the workload is described in its `cpu_baseline.sample`)."""
+    return {"workload": C3_WORKLOAD, "points_per_step": points,
+            "l2": "inputs larger than L2 (the batch workspace of a sweep is tens of GB: top-level workspace_gb)",
+            "parallelism": "sweep points sharded, %d rank(s), no data-path collective" % world}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -722,7 +730,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (Rb 60S+60S pair Hamiltonian built from quantum defects; no dataset)",
-            "config": {"workload": C3_WORKLOAD, "points_per_step": nR},
+            "config": bench_config(args.points, max(1, args.gpus)), "ref_points_per_step": nR,
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": best, "kind": "port",
                              "sample": "%d R points per step (%d per worker), scipy eigsh shift-invert k=250, %d forked "
                                        "workers x 1 BLAS thread, persistent pool, operators inherited"
@@ -825,10 +833,8 @@ def main():
         "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (Rb 60S+60S pair Hamiltonian built from quantum defects by our own defineBasis; no dataset)",
-        "config": {"workload": C3_WORKLOAD,
-                   "points_per_step": args.points, "batch_in_flight": r["batch"],
-                   "l2": "inputs larger than L2 (batch workspace %.1f GB)" % (r["work_bytes"] / 1e9),
-                   "parallelism": "sweep points sharded, %d rank(s), no data-path collective" % world},
+        "config": bench_config(args.points, world),
+        "batch_in_flight": r["batch"], "workspace_gb": round(r["work_bytes"] / 1e9, 1),
         "e2e": {"value": r["e2e_value"], "unit": "solves/s", "h2d_bytes_per_step": r["h2d"],
                 "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms_e2e"] / args.steps,
                 "api": "PairStateInteractions.diagonalise(R, 250) with host buffers"},
