@@ -321,7 +321,9 @@ class AlkaliAtom:
             return ok, [], np.zeros(0, dtype=np.int64)
         ia, ib = ia[ok], ib[ok]
         es = 0.5 if s is None else s
-        E = np.array([self.getEnergy(int(round(t[0])), int(round(t[1])), float(t[2]), s=es) for t in S])
+        E = np.full(len(S), np.nan)
+        for q in np.union1d(ia, ib):       # like the per-element path, only states of allowed pairs are looked up
+            E[q] = self.getEnergy(int(round(S[q, 0])), int(round(S[q, 1])), float(S[q, 2]), s=es)
         swap = E[ia] > E[ib]
         lo, hi = np.where(swap, ib, ia), np.where(swap, ia, ib)
         ucode, _first, inv = _unique_bounded(lo * len(S) + hi)

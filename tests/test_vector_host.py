@@ -217,3 +217,14 @@ def test_index_states_round_trip():
     assert len(np.unique(S, axis=0)) == len(S)                    # every distinct state once
     S0, a0, b0 = arc_b200.AlkaliAtom._index_states(np.zeros((0, 6)))
     assert S0.shape == (0, 3) and len(a0) == len(b0) == 0
+
+
+def test_forbidden_rows_never_touch_the_energies():
+    """getRadialMatrixElement returns 0 for a forbidden pair before it looks at the states
+    (aaf:1016-1019); the vector form must not trip over a state it would never have evaluated."""
+    atom = _patch(arc_b200.Rubidium())
+    rows = [(30, 0, .5, 30, 1, 1.5), (30, 0, .5, 5, 7, 7.5)]          # second row: dl = 7, and l >= n
+    v = atom.radial_elements(rows, 1)
+    assert v[0] != 0 and v[1] == 0
+    with pytest.raises(ValueError):
+        atom.getEnergy(5, 7, 7.5)
