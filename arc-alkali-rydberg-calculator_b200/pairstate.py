@@ -794,6 +794,37 @@ class PairStateInteractions:
         return s
 
     @staticmethod
+    def _greedy_assignment(S):
+        """perm[c] = raw index assigned to position c: entries of S taken in decreasing order, a row and a
+        column used once each (the reference's argsort + rowPicked / columnPicked scan,
+        calculations_atom_pairstate.py:3460-3480).  Fast path: when every position has an overlap above
+        1/2 with exactly one raw state (and vice versa), the scan would take exactly those k entries --
+        it reaches them before any smaller one and none of them share a row or a column -- so they are
+        assigned in one numpy pass.  Any other point (avoided crossings, states entering or leaving the
+        window) runs the full scan, ties included, exactly as before."""
+        k = S.shape[0]
+        big_r, big_c = np.nonzero(S > 0.5)
+        if (len(big_r) == k and np.bincount(big_r, minlength=k).max() == 1
+                and np.bincount(big_c, minlength=k).max() == 1):
+            perm = np.empty(k, dtype=np.int64)
+            perm[big_c] = big_r
+            return perm
+        order_flat = np.argsort(S.ravel())
+        rows_, cols_ = np.unravel_index(order_flat, (k, k))
+        rowPicked = np.zeros(k, dtype=bool)
+        colPicked = np.zeros(k, dtype=bool)
+        perm = np.zeros(k, dtype=np.int64)
+        j, done = k * k - 1, 0
+        while done < k:
+            while rowPicked[rows_[j]] or colPicked[cols_[j]]:
+                j -= 1
+            rowPicked[rows_[j]] = True
+            colPicked[cols_[j]] = True
+            perm[cols_[j]] = rows_[j]
+            done += 1
+        return perm
+
+    @staticmethod
     def _adiabatic_sort(res):
         """Re-order every point's eigenpairs so that index i follows the state adiabatically
         (calculations_atom_pairstate.py:3452-3492): greedy assignment by decreasing squared
@@ -804,19 +835,7 @@ class PairStateInteractions:
         prev = np.arange(k)                       # position -> raw index at the previous point
         for t in range(nR):
             S = res.overlap[t][:, prev]           # S[i, c] = overlap(raw i at t, position c at t-1)
-            order_flat = np.argsort(S.ravel())
-            rows_, cols_ = np.unravel_index(order_flat, (k, k))
-            rowPicked = np.zeros(k, dtype=bool)
-            colPicked = np.zeros(k, dtype=bool)
-            perm = np.zeros(k, dtype=np.int64)
-            j, done = k * k - 1, 0
-            while done < k:
-                while rowPicked[rows_[j]] or colPicked[cols_[j]]:
-                    j -= 1
-                rowPicked[rows_[j]] = True
-                colPicked[cols_[j]] = True
-                perm[cols_[j]] = rows_[j]
-                done += 1
+            perm = PairStateInteractions._greedy_assignment(S)
             res.y[t] = res.y[t][perm]
             res.hl[t] = res.hl[t][perm]
             res.comp_c[t] = res.comp_c[t][perm]

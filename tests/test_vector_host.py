@@ -228,3 +228,41 @@ def test_forbidden_rows_never_touch_the_energies():
     assert v[0] != 0 and v[1] == 0
     with pytest.raises(ValueError):
         atom.getEnergy(5, 7, 7.5)
+
+
+def test_greedy_assignment_fast_path_equals_the_scan():
+    """PairStateInteractions._greedy_assignment: the one-pass assignment of fully dominant points gives
+    what the reference's descending scan gives (calculations_atom_pairstate.py:3460-3480)."""
+    from arc_b200.pairstate import PairStateInteractions as P
+
+    def scan(S):
+        k = S.shape[0]
+        rows_, cols_ = np.unravel_index(np.argsort(S.ravel()), (k, k))
+        rowPicked, colPicked = np.zeros(k, dtype=bool), np.zeros(k, dtype=bool)
+        perm = np.zeros(k, dtype=np.int64)
+        j, done = k * k - 1, 0
+        while done < k:
+            while rowPicked[rows_[j]] or colPicked[cols_[j]]:
+                j -= 1
+            rowPicked[rows_[j]] = colPicked[cols_[j]] = True
+            perm[cols_[j]] = rows_[j]
+            done += 1
+        return perm
+    rng = np.random.default_rng(11)
+    fast = 0
+    for k, nrot, thmax in ((40, 0, 0.0), (40, 30, 0.6), (40, 30, np.pi / 2), (7, 3, 0.5), (1, 0, 0.0), (64, 200, 0.3)):
+        for _ in range(5):
+            Q = np.eye(k)[rng.permutation(k)]
+            for _r in range(nrot):
+                a, b = rng.choice(k, 2, replace=False)
+                th = rng.uniform(0, thmax)
+                G = np.eye(k)
+                G[a, a] = G[b, b] = np.cos(th)
+                G[a, b], G[b, a] = -np.sin(th), np.sin(th)
+                Q = G @ Q
+            S = Q ** 2
+            fast += int((S > 0.5).sum() == k)
+            assert np.array_equal(P._greedy_assignment(S), scan(S))
+    assert fast >= 10                                  # both branches were exercised
+    S = rng.random((9, 9))                             # not overlaps of orthonormal sets: scan branch
+    assert np.array_equal(P._greedy_assignment(S), scan(S))
